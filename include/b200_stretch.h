@@ -1,0 +1,119 @@
+/* b200_stretch.h -- C ABI of the B200-native batched Signalsmith-Stretch hot path.
+ *
+ * One handle = one batch of `batch` independent audio streams that share one configuration
+ * and are driven in lock-step (same call sequence, same buffer sizes), all resident on ONE GPU.
+ * A batch of 1 is exactly one `signalsmith::stretch::SignalsmithStretch<float>` object.
+ *
+ * Every entry point mirrors one method of the reference class
+ *   /root/reference/signalsmith-stretch.h:34-491
+ * and follows the precedent of the reference's own extern "C" wrapper
+ *   /root/reference/web/emscripten/main.cpp:15-77
+ * (scalar arguments, planar float buffers), but handle-based instead of a global singleton
+ * (main.cpp:9) and batched.  Buffers are planar: [batch][channels][samples] float32, the
+ * batched form of the reference's `buffer[channel][index]` convention (README.md:46).
+ *
+ * All functions return 0 on success or a negative B200S_E* code; b200s_last_error() gives text.
+ * The reference's methods return void and never throw (compile.sh:50 -fno-exceptions); error
+ * codes exist here only because a GPU call can fail.  There is NO CPU fallback: without a CUDA
+ * device b200s_create() fails with B200S_ENODEVICE.
+ *
+ * Threading (reference: README.md:93-97): calls on one handle must be serialised by the caller;
+ * different handles are independent.  All work is enqueued on the handle's CUDA stream; host
+ * buffer variants synchronise before returning, *_device variants do not.
+ */
+#ifndef B200_STRETCH_H
+#define B200_STRETCH_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200s_engine b200s_engine;
+
+enum {
+	B200S_OK = 0,
+	B200S_EINVAL = -1,      /* bad argument / not configured */
+	B200S_ENODEVICE = -2,   /* no usable CUDA device: this library has no CPU path */
+	B200S_ECUDA = -3,       /* a CUDA runtime call or kernel failed */
+	B200S_EUNSUPPORTED = -4 /* feature of the reference not available on the GPU path */
+};
+
+/* ---- lifetime: SignalsmithStretch() / SignalsmithStretch(long seed)  (signalsmith-stretch.h:38-39) ---- */
+int b200s_create(int batch, long seed, int device, b200s_engine **out);
+void b200s_destroy(b200s_engine *e);
+const char *b200s_last_error(const b200s_engine *e); /* e may be NULL: error of the last failed create */
+int b200s_version(int *major, int *minor, int *patch); /* reference `version[3]` (:36) = 1.3.2 */
+
+/* Use an existing CUDA stream (a cudaStream_t passed as void*) instead of the handle's own. */
+int b200s_set_stream(b200s_engine *e, void *cuda_stream);
+int b200s_synchronize(b200s_engine *e);
+
+/* ---- configuration: presetDefault / presetCheaper / configure / reset  (:49-94) ---- */
+int b200s_preset_default(b200s_engine *e, int channels, float sample_rate, int split_computation);
+int b200s_preset_cheaper(b200s_engine *e, int channels, float sample_rate, int split_computation);
+int b200s_configure(b200s_engine *e, int channels, int block_samples, int interval_samples, int split_computation);
+int b200s_reset(b200s_engine *e);
+/* Pre-size the per-call scratch so that process() never allocates (the reference asserts
+ * "no allocation in process()", cmd/main-dev.cpp:158-163).  Optional: process() grows on demand. */
+int b200s_reserve(b200s_engine *e, int max_input_samples, int max_output_samples);
+
+/* ---- queries (:42-47, :96-104, :166-168, :205-207) ---- */
+int b200s_batch(const b200s_engine *e);
+int b200s_channels(const b200s_engine *e);
+int b200s_block_samples(const b200s_engine *e);
+int b200s_interval_samples(const b200s_engine *e);
+int b200s_input_latency(const b200s_engine *e);
+int b200s_output_latency(const b200s_engine *e);
+int b200s_split_computation(const b200s_engine *e);
+int b200s_seek_length(const b200s_engine *e);
+int b200s_output_seek_length(const b200s_engine *e, float playback_rate);
+int b200s_fft_samples(const b200s_engine *e);
+int b200s_bands(const b200s_engine *e);
+
+/* ---- parameters, broadcast to every stream of the batch (:107-135) ---- */
+int b200s_set_transpose_factor(b200s_engine *e, float multiplier, float tonality_limit);
+int b200s_set_transpose_semitones(b200s_engine *e, float semitones, float tonality_limit);
+int b200s_set_formant_factor(b200s_engine *e, float multiplier, int compensate_pitch);
+int b200s_set_formant_semitones(b200s_engine *e, float semitones, int compensate_pitch);
+int b200s_set_formant_base(b200s_engine *e, float base_freq);
+/* setFreqMap(std::function) (:120) cannot cross a C ABI (the reference's own wrapper says
+ * "We can't do setFreqMap()", main.cpp:67).  The C++ facade tabulates the callable and passes a
+ * monotone piecewise-linear map here: `n` points, freq_in[i] -> freq_out[i] (both as multiples
+ * of the sample rate, freq_in ascending); linear extrapolation outside.  n == 0 clears it. */
+int b200s_set_freq_map_table(b200s_engine *e, const float *freq_in, const float *freq_out, int n);
+
+/* ---- the hot path (:139-165 seek, :172-204 outputSeek, :209-423 process, :426-464 flush, :467-491 exact) ----
+ * Host-buffer variants: `in`/`out` are host pointers, planar [batch][channels][samples]; the call
+ * copies host->device, runs, copies device->host and synchronises. */
+int b200s_seek(b200s_engine *e, const float *in, int input_samples, double playback_rate);
+int b200s_output_seek(b200s_engine *e, const float *in, int input_length);
+int b200s_process(b200s_engine *e, const float *in, int input_samples, float *out, int output_samples);
+int b200s_flush(b200s_engine *e, float *out, int output_samples, float playback_rate);
+int b200s_exact(b200s_engine *e, const float *in, int input_samples, float *out, int output_samples, int *ok);
+/* Device-buffer variants: pointers are device memory on the handle's GPU, same planar layout;
+ * asynchronous on the handle's stream (input/output buffers must not alias, README.md:46). */
+int b200s_seek_device(b200s_engine *e, const float *d_in, int input_samples, double playback_rate);
+int b200s_process_device(b200s_engine *e, const float *d_in, int input_samples, float *d_out, int output_samples);
+int b200s_flush_device(b200s_engine *e, float *d_out, int output_samples, float playback_rate);
+
+/* ---- measurement helpers (no reference equivalent; used by bench.py) ---- */
+/* CUDA events recorded on the handle's stream around whatever is enqueued in between. */
+int b200s_timer_start(b200s_engine *e);
+int b200s_timer_stop(b200s_engine *e, float *milliseconds); /* synchronises on the stop event */
+/* Kernels launched by this handle since creation (claim for bench.py's "gpu_launches"). */
+long long b200s_kernel_launches(const b200s_engine *e);
+
+/* ---- white-box state for teacher-forced parity tests ----
+ * `what`: 0 input spectrum, 1 prevInput, 2 output (complex: 2*bands floats per stream-channel),
+ *         4 prediction energy (bands floats per stream-channel),
+ *         20 input history (block+interval floats per stream-channel),
+ *         21 pending overlap-add buffer, 22 pending windowProducts (per stream-channel).
+ * Host buffers, layout [batch][channels][...]. */
+int b200s_state_size(const b200s_engine *e, int what); /* floats per stream */
+int b200s_get_state(b200s_engine *e, int what, float *dst);
+int b200s_set_state(b200s_engine *e, int what, const float *src);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,119 @@
+// common.cuh -- shared types of the B200 stretch engine (device + host).
+//
+// Data layout in HBM (all float32 / float2, per engine = per batch of S streams on one GPU):
+//   hist     [S][C][B+H]        input history, most recent sample last        (reference: STFT input ring, B+H+1)
+//   pend     [S][C][B(+H)]      pending overlap-add accumulator, linearised   (reference: STFT output ring)
+//   pendWp   [S][C][B(+H)]      matching windowProducts (one identical copy per channel: single-writer CTAs)
+//   stIn/stPrev/stOut [S][C][K] float2   Band::input / prevInput / output of the last block (:538-542)
+//   stPredE  [S][C][K]          Prediction::energy of the last block (:593)
+// and per process() call scratch, F = blocks in the call:
+//   spec     [S][2F][C][K] float2   analysis spectra (slot 2f: block f, slot 2f+1: its re-analysed predecessor)
+//   cE       [S][F][C][K]           Prediction::energy
+//   cPI,cFT,cT1,cT2 [S][F][C][K] float2   Prediction::input, freqTwist, short/long vertical twists
+//   Y        [S][F][C][K] float2    final Band::output of every block
+#pragma once
+
+#ifdef B200S_EMU
+#include "cuda_emu.h" // tests/cuda_emu: thread-per-CUDA-thread CPU emulator, TEST BUILDS ONLY
+#else
+#include <cuda_runtime.h>
+#define B200S_SHARED __shared__
+#define B200S_DYN_SHARED extern __shared__ float4 dyn_smem[];
+#define B200S_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#include <stdint.h>
+
+namespace b200s {
+
+// ---- constants of the reference ----
+#define B200S_NOISE_FLOOR 1e-15f      // signalsmith-stretch.h:508
+#define B200S_MAX_CLEAN_STRETCH 2.0f  // :509
+#define B200S_ALMOST_ZERO 1e-30f      // dependency's windowProducts floor (measured)
+#define B200S_NEVER (1ll << 60)       // blockProcess.samplesSinceLast initial value (:496, SIZE_MAX there)
+
+enum FrameFlags {
+	FR_NEW_SPECTRUM = 1, // :299
+	FR_REANALYSE = 2,    // :303
+	FR_MAPPED = 4,       // :300
+	FR_FORMANTS = 8,     // :310
+	FR_RANDOM = 16       // :639
+};
+
+// static configuration of one engine
+struct Cfg {
+	int S, C;          // streams, channels
+	int B, H, N, K;    // block, interval, fftSamples, bands (= N/2 = complex FFT size)
+	int L;             // longVerticalStep = round(N/H) (:637)
+	int split;         // splitComputation
+	int histLen;       // B + H
+	int pendLen;       // B (+ H when split)
+	int addOff;        // where a block lands in `pend` (H when split, :294-297)
+	int o;             // analysis/synthesis offset = B/2
+	int nStages;       // Stockham stages of the K-point complex FFT
+	int radix[20];
+};
+
+// user parameters (:107-135), broadcast to every stream
+struct Params {
+	float freqMultiplier, freqTonalityLimit;
+	float formantMultiplier, invFormantMultiplier, formantBaseFreq;
+	int formantCompensation;
+	int mapN;                 // >0: custom piecewise-linear frequency map (setFreqMap, :120)
+	const float *mapIn, *mapOut;
+};
+
+// per-stream block scheduler state (:494-529)
+struct Sched {
+	long long samplesSinceLast;
+	long long silenceCounter;
+	int prevInputOffset;
+	int didSeek;
+	int silenceFirst;
+	float seekTimeFactor;
+};
+
+// one block of the schedule (:281-319)
+struct Frame {
+	int t;           // output index within the call at which the block triggers
+	int inputOffset; // :288
+	int flags;
+	float timeFactor; // :312, before the clamp of :638
+	int inSlot, prevSlot; // spectrum slots: 0 = stIn, 1 = stPrev, 2+2f / 3+2f = this call's analyses
+};
+
+// per-stream result of the planner for one process() call
+struct Call {
+	int bypass;   // silence bypass (:240-271)
+	int nFrames;
+	int finalIn, finalPrev; // slots that become stIn / stPrev after the call
+};
+
+// everything a kernel needs, passed by value
+struct Ctx {
+	Cfg cfg;
+	Params prm;
+	// tables
+	const float *window, *winProd, *wpReset;
+	const float2 *rot, *twiddle, *pretw;
+	// state
+	Sched *sched;
+	float *histCur, *histNext;
+	float *pend, *pendWp;
+	float2 *stIn, *stPrev, *stOut;
+	float *stPredE;
+	// call scratch
+	int maxFrames;
+	Frame *frames; // [S][maxFrames]
+	Call *call;    // [S]
+	float2 *spec, *Y, *cPI, *cFT, *cT1, *cT2;
+	float *cE;
+	// I/O of the current call
+	const float *in;
+	float *out;
+	int nIn, nOut;
+	long long inStreamStride, outStreamStride; // floats between streams
+	int inChanStride, outChanStride;           // floats between channels
+};
+
+} // namespace b200s

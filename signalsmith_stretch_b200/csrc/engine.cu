@@ -1,0 +1,731 @@
+// engine.cu -- host side of the B200 stretch engine + the extern "C" ABI of include/b200_stretch.h.
+//
+// The host does no DSP: it sizes buffers, builds the constant tables once per configure() and
+// enqueues kernels on one CUDA stream.  Even the block scheduler runs on the device (k_plan), so
+// a process() call is a fixed, sync-free launch sequence:
+//     k_plan -> k_analyse -> k_prep -> k_chain -> k_synth -> k_commit
+// Reference for every step: /root/reference/signalsmith-stretch.h (cited per kernel in kernels.cuh).
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_stretch.h"
+#include "kernels.cuh"
+
+using namespace b200s;
+
+static std::string g_createError;
+
+struct b200s_engine {
+	int S = 0, device = 0;
+	long seed = 0;
+	bool configured = false;
+	Cfg cfg;
+	Params prm;
+	cudaStream_t stream = 0;
+	bool ownStream = false;
+	cudaEvent_t evStart = 0, evStop = 0;
+	long long launches = 0;
+	std::string err;
+
+	// tables
+	float *dWindow = 0, *dWinProd = 0, *dWpReset = 0;
+	float2 *dRot = 0, *dTwiddle = 0, *dPretw = 0;
+	float *dMapIn = 0, *dMapOut = 0;
+	// state
+	Sched *dSched = 0;
+	float *dHist[2] = {0, 0};
+	int histCur = 0;
+	float *dPend = 0, *dPendWp = 0;
+	float2 *dStIn = 0, *dStPrev = 0, *dStOut = 0;
+	float *dStPredE = 0;
+	// call scratch
+	int maxFrames = 0;
+	Frame *dFrames = 0;
+	Call *dCall = 0;
+	float2 *dSpec = 0, *dY = 0, *dPI = 0, *dFT = 0, *dT1 = 0, *dT2 = 0;
+	float *dE = 0;
+	// staging for the host-buffer API and for flush/outputSeek
+	float *dIn = 0, *dOut = 0, *dZero = 0, *dTmp = 0;
+	size_t inCap = 0, outCap = 0, zeroCap = 0, tmpCap = 0;
+};
+
+#define CK(call)                                                                                   \
+	do {                                                                                           \
+		cudaError_t _e = (call);                                                                   \
+		if (_e != cudaSuccess) {                                                                   \
+			e->err = std::string(#call) + ": " + cudaGetErrorString(_e);                           \
+			return B200S_ECUDA;                                                                    \
+		}                                                                                          \
+	} while (0)
+#define CKL()                                                                                      \
+	do {                                                                                           \
+		++e->launches;                                                                             \
+		CK(cudaGetLastError());                                                                    \
+	} while (0)
+#define NEED_CFG()                                                                                 \
+	do {                                                                                           \
+		if (!e) return B200S_EINVAL;                                                               \
+		if (!e->configured) {                                                                      \
+			e->err = "engine not configured";                                                      \
+			return B200S_EINVAL;                                                                   \
+		}                                                                                          \
+	} while (0)
+
+template <typename T>
+static int dalloc(b200s_engine *e, T **p, size_t n) {
+	if (*p) cudaFree(*p);
+	*p = 0;
+	CK(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+	return 0;
+}
+template <typename T>
+static void dfree(T *&p) {
+	if (p) cudaFree(p);
+	p = 0;
+}
+
+static void free_all(b200s_engine *e) {
+	dfree(e->dWindow); dfree(e->dWinProd); dfree(e->dWpReset); dfree(e->dRot); dfree(e->dTwiddle); dfree(e->dPretw);
+	dfree(e->dSched); dfree(e->dHist[0]); dfree(e->dHist[1]); dfree(e->dPend); dfree(e->dPendWp);
+	dfree(e->dStIn); dfree(e->dStPrev); dfree(e->dStOut); dfree(e->dStPredE);
+	dfree(e->dFrames); dfree(e->dCall); dfree(e->dSpec); dfree(e->dY); dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dE);
+	dfree(e->dIn); dfree(e->dOut); dfree(e->dZero); dfree(e->dTmp);
+	e->maxFrames = 0;
+	e->inCap = e->outCap = e->zeroCap = e->tmpCap = 0;
+}
+
+static Ctx make_ctx(b200s_engine *e) {
+	Ctx x;
+	memset(&x, 0, sizeof(x));
+	x.cfg = e->cfg;
+	x.prm = e->prm;
+	x.prm.mapIn = e->dMapIn;
+	x.prm.mapOut = e->dMapOut;
+	x.window = e->dWindow; x.winProd = e->dWinProd; x.wpReset = e->dWpReset;
+	x.rot = e->dRot; x.twiddle = e->dTwiddle; x.pretw = e->dPretw;
+	x.sched = e->dSched;
+	x.histCur = e->dHist[e->histCur]; x.histNext = e->dHist[e->histCur ^ 1];
+	x.pend = e->dPend; x.pendWp = e->dPendWp;
+	x.stIn = e->dStIn; x.stPrev = e->dStPrev; x.stOut = e->dStOut; x.stPredE = e->dStPredE;
+	x.maxFrames = e->maxFrames;
+	x.frames = e->dFrames; x.call = e->dCall;
+	x.spec = e->dSpec; x.Y = e->dY; x.cPI = e->dPI; x.cFT = e->dFT; x.cT1 = e->dT1; x.cT2 = e->dT2; x.cE = e->dE;
+	return x;
+}
+
+// complex FFT size the dependency picks for a block: 2^k * {1,3,5} (measured)
+static int fast_size_above(int n) {
+	int p = 1;
+	while (p < 16 && p < n) p *= 2;
+	while (8 * p < n) p *= 2;
+	int m = (n + p - 1) / p;
+	if (m == 7) m = 8;
+	return m * p;
+}
+static double bessel0(double x) {
+	double sum = 1, term = 1, q = x * x * 0.25;
+	for (int k = 1; k < 200; ++k) {
+		term *= q / (double(k) * k);
+		sum += term;
+		if (term < sum * 1e-17) break;
+	}
+	return sum;
+}
+
+static const int kThreads = 256;
+static size_t smem_analyse(const Cfg &g) { return sizeof(float2) * 2 * g.K; }
+static size_t smem_prep(const Cfg &g) { return sizeof(float) * (7 * (size_t)g.K + 8); }
+static size_t smem_synth(const Cfg &g) { return sizeof(float2) * 2 * g.K + sizeof(float) * 2 * g.pendLen; }
+
+static int reset_impl(b200s_engine *e, bool full) {
+	Ctx x = make_ctx(e);
+	B200S_LAUNCH(k_reset_stft, dim3(e->S), dim3(kThreads), 0, e->stream, x);
+	CKL();
+	B200S_LAUNCH(k_reset_bands, dim3(e->S), dim3(kThreads), 0, e->stream, x, full ? 15 : 6);
+	CKL();
+	return 0;
+}
+
+static int configure_impl(b200s_engine *e, int channels, int block, int interval, int split) {
+	if (!e) return B200S_EINVAL;
+	if (channels < 1 || block < 4 || interval < 1 || interval > block) {
+		e->err = "configure: need channels >= 1, block >= 4, 1 <= interval <= block";
+		return B200S_EINVAL;
+	}
+	Cfg g;
+	memset(&g, 0, sizeof(g));
+	g.S = e->S;
+	g.C = channels;
+	g.B = block;
+	g.H = interval;
+	g.N = 2 * fast_size_above((block + 1) / 2); // DynamicSTFT::configure (App. B)
+	g.K = g.N / 2;
+	g.L = (int)std::round(float(g.N) / float(g.H)); // :636-637
+	g.split = split ? 1 : 0;
+	g.histLen = g.B + g.H;
+	g.pendLen = g.B + (g.split ? g.H : 0);
+	g.addOff = g.split ? g.H : 0;
+	g.o = g.B / 2;
+	{ // Stockham plan: radix 4s, one radix 2 if needed, the odd radix last
+		int k = g.K, odd = 1;
+		if (k % 3 == 0) { odd = 3; k /= 3; }
+		else if (k % 5 == 0) { odd = 5; k /= 5; }
+		int n = 0;
+		while (k % 4 == 0) { g.radix[n++] = 4; k /= 4; }
+		if (k % 2 == 0) { g.radix[n++] = 2; k /= 2; }
+		if (k != 1) { e->err = "unsupported FFT size"; return B200S_EUNSUPPORTED; }
+		if (odd > 1) g.radix[n++] = odd;
+		g.nStages = n;
+	}
+	if (g.L < 1 || g.L > 8 || (channels > 2)) {
+		e->err = "GPU path supports 1-2 channels and block/interval ratios with round(fftSamples/interval) in 1..8";
+		return B200S_EUNSUPPORTED;
+	}
+	if (smem_prep(g) > 220 * 1024 || smem_synth(g) > 220 * 1024) {
+		e->err = "block too large for the shared-memory FFT (bands must be <= ~6144)";
+		return B200S_EUNSUPPORTED;
+	}
+	CK(cudaSetDevice(e->device));
+	CK(cudaStreamSynchronize(e->stream));
+	free_all(e);
+	e->cfg = g;
+
+	// ---- tables.  Window: Kaiser, the dependency's bandwidth heuristic, forced perfect reconstruction (App. B)
+	std::vector<float> window(g.B), winProd(g.B), wpReset(g.pendLen);
+	{
+		double bw = double(g.B) / double(g.H);
+		bw += 8 / ((bw + 3) * (bw + 3)) + 0.25 * std::max(3 - bw, 0.0);
+		bw = std::max(bw, 2.0);
+		double beta = M_PI * std::sqrt(bw * bw * 0.25 - 1);
+		std::vector<double> w(g.B);
+		for (int i = 0; i < g.B; ++i) {
+			double r = (2.0 * i + 1) / g.B - 1;
+			w[i] = bessel0(beta * std::sqrt(std::max(0.0, 1 - r * r))) / bessel0(beta);
+		}
+		for (int i = 0; i < g.H && i < g.B; ++i) {
+			double s2 = 0;
+			for (int k = i; k < g.B; k += g.H) s2 += w[k] * w[k];
+			double f = 1 / std::sqrt(s2);
+			for (int k = i; k < g.B; k += g.H) w[k] *= f;
+		}
+		for (int i = 0; i < g.B; ++i) {
+			window[i] = float(w[i]);
+			winProd[i] = window[i] * window[i] * float(g.N);
+		}
+		for (int i = 0; i < g.pendLen; ++i) { // DynamicSTFT::reset(0.1) then moveOutput(H)
+			int ring = i + g.H;
+			if (ring < g.B) {
+				float sum = 0;
+				for (int k = ring; k < g.B; k += g.H) sum += window[k] * window[k];
+				wpReset[i] = 0.1f * float(g.N) * sum + B200S_ALMOST_ZERO;
+			} else {
+				wpReset[i] = B200S_ALMOST_ZERO;
+			}
+		}
+	}
+	std::vector<float2> rot(g.K), tw(g.K), pre(g.K);
+	{ // :647-655, the reference's own float recurrence (its rounding is part of the result)
+		auto b2f = [&](float b) { return (b + 0.5f) / float(g.N); };
+		std::complex<float> r = std::polar(1.0f, b2f(0) * float(g.H) * float(2 * M_PI));
+		float freqStep = b2f(1) - b2f(0);
+		std::complex<float> step = std::polar(1.0f, freqStep * float(g.H) * float(2 * M_PI));
+		for (int b = 0; b < g.K; ++b) {
+			rot[b] = make_float2(r.real(), r.imag());
+			r = std::complex<float>(r.real() * step.real() - r.imag() * step.imag(), r.real() * step.imag() + r.imag() * step.real());
+		}
+		for (int t = 0; t < g.K; ++t) {
+			tw[t] = make_float2(float(std::cos(-2.0 * M_PI * t / g.K)), float(std::sin(-2.0 * M_PI * t / g.K)));
+			pre[t] = make_float2(float(std::cos(-M_PI * t / g.N)), float(std::sin(-M_PI * t / g.N)));
+		}
+	}
+	int rc;
+	if ((rc = dalloc(e, &e->dWindow, g.B))) return rc;
+	if ((rc = dalloc(e, &e->dWinProd, g.B))) return rc;
+	if ((rc = dalloc(e, &e->dWpReset, g.pendLen))) return rc;
+	if ((rc = dalloc(e, &e->dRot, g.K))) return rc;
+	if ((rc = dalloc(e, &e->dTwiddle, g.K))) return rc;
+	if ((rc = dalloc(e, &e->dPretw, g.K))) return rc;
+	CK(cudaMemcpy(e->dWindow, window.data(), sizeof(float) * g.B, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(e->dWinProd, winProd.data(), sizeof(float) * g.B, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(e->dWpReset, wpReset.data(), sizeof(float) * g.pendLen, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(e->dRot, rot.data(), sizeof(float2) * g.K, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(e->dTwiddle, tw.data(), sizeof(float2) * g.K, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(e->dPretw, pre.data(), sizeof(float2) * g.K, cudaMemcpyHostToDevice));
+
+	// ---- state
+	const size_t SC = (size_t)g.S * g.C;
+	if ((rc = dalloc(e, &e->dSched, g.S))) return rc;
+	if ((rc = dalloc(e, &e->dHist[0], SC * g.histLen))) return rc;
+	if ((rc = dalloc(e, &e->dHist[1], SC * g.histLen))) return rc;
+	if ((rc = dalloc(e, &e->dPend, SC * g.pendLen))) return rc;
+	if ((rc = dalloc(e, &e->dPendWp, SC * g.pendLen))) return rc;
+	if ((rc = dalloc(e, &e->dStIn, SC * g.K))) return rc;
+	if ((rc = dalloc(e, &e->dStPrev, SC * g.K))) return rc;
+	if ((rc = dalloc(e, &e->dStOut, SC * g.K))) return rc;
+	if ((rc = dalloc(e, &e->dStPredE, SC * g.K))) return rc;
+	if ((rc = dalloc(e, &e->dCall, g.S))) return rc;
+	CK(cudaMemset(e->dStPredE, 0, sizeof(float) * SC * g.K));
+	CK(cudaMemset(e->dHist[1], 0, sizeof(float) * SC * g.histLen));
+	{
+		std::vector<Sched> sc(g.S);
+		for (auto &s : sc) {
+			s.samplesSinceLast = B200S_NEVER;
+			s.silenceCounter = 0;
+			s.prevInputOffset = -1;
+			s.didSeek = 0;
+			s.silenceFirst = 1;
+			s.seekTimeFactor = 1;
+		}
+		CK(cudaMemcpy(e->dSched, sc.data(), sizeof(Sched) * g.S, cudaMemcpyHostToDevice));
+	}
+	e->histCur = 0;
+#ifndef B200S_EMU
+	CK(cudaFuncSetAttribute(k_analyse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_analyse(g)));
+	CK(cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep(g)));
+	CK(cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_synth(g)));
+	CK(cudaFuncSetAttribute(k_flush_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * g.B)));
+#endif
+	e->configured = true;
+	return reset_impl(e, true);
+}
+
+static int frames_bound(const Cfg &g, int nOut) { return nOut <= 0 ? 0 : (nOut + g.H - 1) / g.H + 1; }
+
+static int ensure_scratch(b200s_engine *e, int nOut) {
+	const Cfg &g = e->cfg;
+	int need = std::max(frames_bound(g, nOut), 1);
+	if (need <= e->maxFrames) return 0;
+	CK(cudaStreamSynchronize(e->stream));
+	const size_t n = (size_t)g.S * need * g.C * g.K;
+	int rc;
+	if ((rc = dalloc(e, &e->dFrames, (size_t)g.S * need))) return rc;
+	if ((rc = dalloc(e, &e->dSpec, 2 * n))) return rc;
+	if ((rc = dalloc(e, &e->dY, n))) return rc;
+	if ((rc = dalloc(e, &e->dPI, n))) return rc;
+	if ((rc = dalloc(e, &e->dFT, n))) return rc;
+	if ((rc = dalloc(e, &e->dT1, n))) return rc;
+	if ((rc = dalloc(e, &e->dT2, n))) return rc;
+	if ((rc = dalloc(e, &e->dE, n))) return rc;
+	e->maxFrames = need;
+	return 0;
+}
+static int ensure_buf(b200s_engine *e, float **p, size_t *cap, size_t n, bool zero) {
+	if (n <= *cap && *p) return 0;
+	CK(cudaStreamSynchronize(e->stream));
+	int rc;
+	if ((rc = dalloc(e, p, n))) return rc;
+	*cap = n;
+	if (zero) CK(cudaMemset(*p, 0, sizeof(float) * std::max<size_t>(n, 1)));
+	return 0;
+}
+
+typedef void (*ChainKernel)(Ctx);
+template <int CT>
+static ChainKernel chain_kernel_for(int L) {
+	switch (L) {
+	case 1: return k_chain<CT, 1>;
+	case 2: return k_chain<CT, 2>;
+	case 3: return k_chain<CT, 3>;
+	case 4: return k_chain<CT, 4>;
+	case 5: return k_chain<CT, 5>;
+	case 6: return k_chain<CT, 6>;
+	case 7: return k_chain<CT, 7>;
+	default: return k_chain<CT, 8>;
+	}
+}
+
+// process() on device buffers with explicit strides (floats between channels / streams)
+static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, long long inStreamStride, int nIn,
+                        float *dOut, int outChanStride, long long outStreamStride, int nOut) {
+	const Cfg &g = e->cfg;
+	if (nIn < 0 || nOut < 0) {
+		e->err = "process: negative sample count";
+		return B200S_EINVAL;
+	}
+	int rc;
+	if ((rc = ensure_scratch(e, nOut))) return rc;
+	Ctx x = make_ctx(e);
+	x.in = dIn; x.out = dOut; x.nIn = nIn; x.nOut = nOut;
+	x.inChanStride = inChanStride; x.inStreamStride = inStreamStride;
+	x.outChanStride = outChanStride; x.outStreamStride = outStreamStride;
+	const int F = frames_bound(g, nOut);
+	B200S_LAUNCH(k_plan, dim3(g.S), dim3(kThreads), 0, e->stream, x);
+	CKL();
+	if (F > 0) {
+		B200S_LAUNCH(k_analyse, dim3(2 * F, g.C, g.S), dim3(kThreads), smem_analyse(g), e->stream, x);
+		CKL();
+		B200S_LAUNCH(k_prep, dim3(F, g.S), dim3(kThreads), smem_prep(g), e->stream, x);
+		CKL();
+		const int warps = 4;
+		dim3 grid((g.S + warps - 1) / warps), block(32 * warps);
+		ChainKernel kc = g.C == 1 ? chain_kernel_for<1>(g.L) : chain_kernel_for<2>(g.L);
+		B200S_LAUNCH(kc, grid, block, 0, e->stream, x);
+		CKL();
+	}
+	B200S_LAUNCH(k_synth, dim3(g.C, g.S), dim3(kThreads), smem_synth(g), e->stream, x);
+	CKL();
+	B200S_LAUNCH(k_commit, dim3(g.S), dim3(kThreads), 0, e->stream, x);
+	CKL();
+	e->histCur ^= 1;
+	return 0;
+}
+
+static int seek_impl(b200s_engine *e, const float *dIn, int chanStride, long long streamStride, int n, double playbackRate) {
+	const Cfg &g = e->cfg;
+	Ctx x = make_ctx(e);
+	x.in = dIn; x.nIn = n; x.inChanStride = chanStride; x.inStreamStride = streamStride;
+	float stf = (playbackRate * g.H > 1) ? float(1 / playbackRate) : float(g.H); // :164
+	B200S_LAUNCH(k_seek, dim3(g.S), dim3(kThreads), 0, e->stream, x, stf);
+	CKL();
+	return 0;
+}
+
+static int flush_impl(b200s_engine *e, float *dOut, int outChanStride, long long outStreamStride, int nOut, float playbackRate) {
+	const Cfg &g = e->cfg;
+	int rc;
+	int outputBlock = std::max(0, nOut - g.H); // :439
+	if (outputBlock > 0) {
+		int nIn = int(outputBlock * playbackRate); // :440
+		if (nIn < 0) nIn = 0;
+		size_t zn = (size_t)g.S * g.C * std::max(nIn, 1);
+		if ((rc = ensure_buf(e, &e->dZero, &e->zeroCap, zn, true))) return rc;
+		if ((rc = process_impl(e, e->dZero, nIn, (long long)g.C * nIn, nIn, dOut, outChanStride, outStreamStride, outputBlock))) return rc;
+	}
+	int tail = nOut - outputBlock;
+	Ctx x = make_ctx(e);
+	x.out = dOut; x.outChanStride = outChanStride; x.outStreamStride = outStreamStride;
+	if (tail > 0) {
+		B200S_LAUNCH(k_flush_tail, dim3(g.C, g.S), dim3(kThreads), sizeof(float) * g.B, e->stream, x, outputBlock, tail);
+		CKL();
+	}
+	return reset_impl(e, false); // stft.reset(0.1); prevInput = output = 0 (:456-463)
+}
+
+static int output_seek_impl(b200s_engine *e, const float *dIn, int chanStride, long long streamStride, int inputLength) {
+	const Cfg &g = e->cfg;
+	int rc;
+	if ((rc = reset_impl(e, true))) return rc; // :175
+	const int inLat = g.B - g.B / 2, outLat = g.B / 2 + (g.split ? g.H : 0);
+	int surplus = std::max(inputLength - inLat, 0);            // :177
+	float playbackRate = surplus / float(outLat);              // :178
+	int seekSamples = inputLength - surplus;                   // :181
+	if ((rc = seek_impl(e, dIn, chanStride, streamStride, seekSamples, playbackRate))) return rc;
+	size_t tn = (size_t)g.S * g.C * outLat;
+	if ((rc = ensure_buf(e, &e->dTmp, &e->tmpCap, tn, false))) return rc;
+	if ((rc = process_impl(e, dIn + seekSamples, chanStride, streamStride, surplus, e->dTmp, outLat, (long long)g.C * outLat, outLat))) return rc; // :196
+	Ctx x = make_ctx(e);
+	B200S_LAUNCH(k_add_output, dim3(g.C, g.S), dim3(kThreads), 0, e->stream, x, e->dTmp, outLat); // :199-203
+	CKL();
+	return 0;
+}
+
+static int stage_in(b200s_engine *e, const float *in, int n) {
+	size_t cnt = (size_t)e->cfg.S * e->cfg.C * std::max(n, 1);
+	int rc;
+	if ((rc = ensure_buf(e, &e->dIn, &e->inCap, cnt, false))) return rc;
+	if (n > 0) CK(cudaMemcpyAsync(e->dIn, in, sizeof(float) * (size_t)e->cfg.S * e->cfg.C * n, cudaMemcpyHostToDevice, e->stream));
+	return 0;
+}
+static int stage_out(b200s_engine *e, int n) {
+	size_t cnt = (size_t)e->cfg.S * e->cfg.C * std::max(n, 1);
+	return ensure_buf(e, &e->dOut, &e->outCap, cnt, false);
+}
+static int fetch_out(b200s_engine *e, float *out, int n) {
+	if (n > 0) CK(cudaMemcpyAsync(out, e->dOut, sizeof(float) * (size_t)e->cfg.S * e->cfg.C * n, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return 0;
+}
+
+// =================================================================================================
+// extern "C" ABI
+// =================================================================================================
+extern "C" {
+
+int b200s_create(int batch, long seed, int device, b200s_engine **out) {
+	if (!out || batch < 1) {
+		g_createError = "b200s_create: bad arguments";
+		return B200S_EINVAL;
+	}
+	*out = 0;
+	int n = 0;
+	cudaError_t ce = cudaGetDeviceCount(&n);
+	if (ce != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+		g_createError = std::string("no usable CUDA device (this library has no CPU path): ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device index out of range");
+		return B200S_ENODEVICE;
+	}
+	b200s_engine *e = new b200s_engine();
+	e->S = batch;
+	e->seed = seed;
+	e->device = device;
+	memset(&e->cfg, 0, sizeof(e->cfg));
+	memset(&e->prm, 0, sizeof(e->prm));
+	e->prm.freqMultiplier = 1;
+	e->prm.freqTonalityLimit = 0.5f; // :513
+	e->prm.formantMultiplier = e->prm.invFormantMultiplier = 1;
+	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaEventCreate(&e->evStart) != cudaSuccess || cudaEventCreate(&e->evStop) != cudaSuccess) {
+		g_createError = "CUDA stream/event creation failed";
+		delete e;
+		return B200S_ECUDA;
+	}
+	e->ownStream = true;
+	*out = e;
+	return 0;
+}
+void b200s_destroy(b200s_engine *e) {
+	if (!e) return;
+	cudaSetDevice(e->device);
+	cudaStreamSynchronize(e->stream);
+	free_all(e);
+	dfree(e->dMapIn);
+	dfree(e->dMapOut);
+	if (e->evStart) cudaEventDestroy(e->evStart);
+	if (e->evStop) cudaEventDestroy(e->evStop);
+	if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
+	delete e;
+}
+const char *b200s_last_error(const b200s_engine *e) { return e ? e->err.c_str() : g_createError.c_str(); }
+int b200s_version(int *major, int *minor, int *patch) {
+	if (major) *major = 1;
+	if (minor) *minor = 3;
+	if (patch) *patch = 2;
+	return 0;
+}
+int b200s_set_stream(b200s_engine *e, void *cuda_stream) {
+	if (!e) return B200S_EINVAL;
+	CK(cudaStreamSynchronize(e->stream));
+	if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
+	e->stream = (cudaStream_t)cuda_stream;
+	e->ownStream = false;
+	return 0;
+}
+int b200s_synchronize(b200s_engine *e) {
+	if (!e) return B200S_EINVAL;
+	CK(cudaStreamSynchronize(e->stream));
+	return 0;
+}
+
+int b200s_preset_default(b200s_engine *e, int channels, float sr, int split) {
+	return configure_impl(e, channels, int(sr * 0.12), int(sr * 0.03), split); // :63-65
+}
+int b200s_preset_cheaper(b200s_engine *e, int channels, float sr, int split) {
+	return configure_impl(e, channels, int(sr * 0.1), int(sr * 0.04), split); // :66-68
+}
+int b200s_configure(b200s_engine *e, int channels, int block, int interval, int split) { return configure_impl(e, channels, block, interval, split); }
+int b200s_reset(b200s_engine *e) {
+	NEED_CFG();
+	return reset_impl(e, true);
+}
+int b200s_reserve(b200s_engine *e, int maxIn, int maxOut) {
+	NEED_CFG();
+	int rc;
+	if ((rc = ensure_scratch(e, maxOut))) return rc;
+	if ((rc = stage_in(e, 0, 0))) return rc;
+	size_t ci = (size_t)e->cfg.S * e->cfg.C * std::max(maxIn, 1), co = (size_t)e->cfg.S * e->cfg.C * std::max(maxOut, 1);
+	if ((rc = ensure_buf(e, &e->dIn, &e->inCap, ci, false))) return rc;
+	return ensure_buf(e, &e->dOut, &e->outCap, co, false);
+}
+
+int b200s_batch(const b200s_engine *e) { return e ? e->S : 0; }
+int b200s_channels(const b200s_engine *e) { return e && e->configured ? e->cfg.C : 0; }
+int b200s_block_samples(const b200s_engine *e) { return e && e->configured ? e->cfg.B : 0; }
+int b200s_interval_samples(const b200s_engine *e) { return e && e->configured ? e->cfg.H : 0; }
+int b200s_input_latency(const b200s_engine *e) { return e && e->configured ? e->cfg.B - e->cfg.B / 2 : 0; }                       // :42-44
+int b200s_output_latency(const b200s_engine *e) { return e && e->configured ? e->cfg.B / 2 + (e->cfg.split ? e->cfg.H : 0) : 0; } // :45-47
+int b200s_split_computation(const b200s_engine *e) { return e && e->configured ? e->cfg.split : 0; }
+int b200s_seek_length(const b200s_engine *e) { return e && e->configured ? e->cfg.B + e->cfg.H : 0; } // :166-168
+int b200s_output_seek_length(const b200s_engine *e, float rate) {                                       // :205-207
+	return e && e->configured ? int(b200s_input_latency(e) + rate * b200s_output_latency(e)) : 0;
+}
+int b200s_fft_samples(const b200s_engine *e) { return e && e->configured ? e->cfg.N : 0; }
+int b200s_bands(const b200s_engine *e) { return e && e->configured ? e->cfg.K : 0; }
+
+int b200s_set_transpose_factor(b200s_engine *e, float multiplier, float tonality) { // :107-115
+	if (!e) return B200S_EINVAL;
+	e->prm.freqMultiplier = multiplier;
+	if (tonality > 0) e->prm.freqTonalityLimit = tonality / std::sqrt(multiplier);
+	else e->prm.freqTonalityLimit = 1;
+	e->prm.mapN = 0;
+	return 0;
+}
+int b200s_set_transpose_semitones(b200s_engine *e, float semitones, float tonality) { // :116-118
+	return b200s_set_transpose_factor(e, std::pow(2, semitones / 12), tonality);
+}
+int b200s_set_formant_factor(b200s_engine *e, float multiplier, int comp) { // :124-128
+	if (!e) return B200S_EINVAL;
+	e->prm.formantMultiplier = multiplier;
+	e->prm.invFormantMultiplier = 1 / multiplier;
+	e->prm.formantCompensation = comp ? 1 : 0;
+	return 0;
+}
+int b200s_set_formant_semitones(b200s_engine *e, float semitones, int comp) { // :129-131
+	return b200s_set_formant_factor(e, std::pow(2, semitones / 12), comp);
+}
+int b200s_set_formant_base(b200s_engine *e, float f) { // :133-135
+	if (!e) return B200S_EINVAL;
+	e->prm.formantBaseFreq = f;
+	return 0;
+}
+int b200s_set_freq_map_table(b200s_engine *e, const float *fin, const float *fout, int n) {
+	if (!e || n < 0 || (n > 0 && (!fin || !fout))) return B200S_EINVAL;
+	CK(cudaStreamSynchronize(e->stream));
+	dfree(e->dMapIn);
+	dfree(e->dMapOut);
+	e->prm.mapN = 0;
+	if (n == 0) return 0;
+	int rc;
+	if ((rc = dalloc(e, &e->dMapIn, n))) return rc;
+	if ((rc = dalloc(e, &e->dMapOut, n))) return rc;
+	CK(cudaMemcpy(e->dMapIn, fin, sizeof(float) * n, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(e->dMapOut, fout, sizeof(float) * n, cudaMemcpyHostToDevice));
+	e->prm.mapN = n;
+	return 0;
+}
+
+static int check_formant_support(b200s_engine *e) {
+	const Params &p = e->prm;
+	bool mapped = p.mapN > 0 || p.freqMultiplier != 1.0f;
+	bool formants = p.formantMultiplier != 1.0f || (p.formantCompensation && mapped);
+	if (formants && !(p.formantBaseFreq > 0)) {
+		e->err = "formant processing on the GPU path needs setFormantBase(f > 0); automatic pitch detection (setFormantBase(0)) is not implemented yet";
+		return B200S_EUNSUPPORTED;
+	}
+	return 0;
+}
+
+int b200s_seek_device(b200s_engine *e, const float *dIn, int n, double rate) {
+	NEED_CFG();
+	if (n < 0) return B200S_EINVAL;
+	return seek_impl(e, dIn, n, (long long)e->cfg.C * n, n, rate);
+}
+int b200s_process_device(b200s_engine *e, const float *dIn, int nIn, float *dOut, int nOut) {
+	NEED_CFG();
+	int rc;
+	if ((rc = check_formant_support(e))) return rc;
+	return process_impl(e, dIn, nIn, (long long)e->cfg.C * nIn, nIn, dOut, nOut, (long long)e->cfg.C * nOut, nOut);
+}
+int b200s_flush_device(b200s_engine *e, float *dOut, int nOut, float rate) {
+	NEED_CFG();
+	if (nOut < 0) return B200S_EINVAL;
+	return flush_impl(e, dOut, nOut, (long long)e->cfg.C * nOut, nOut, rate);
+}
+int b200s_seek(b200s_engine *e, const float *in, int n, double rate) {
+	NEED_CFG();
+	if (n < 0) return B200S_EINVAL;
+	int rc;
+	if ((rc = stage_in(e, in, n))) return rc;
+	if ((rc = seek_impl(e, e->dIn, n, (long long)e->cfg.C * n, n, rate))) return rc;
+	CK(cudaStreamSynchronize(e->stream));
+	return 0;
+}
+int b200s_process(b200s_engine *e, const float *in, int nIn, float *out, int nOut) {
+	NEED_CFG();
+	int rc;
+	if ((rc = check_formant_support(e))) return rc;
+	if ((rc = stage_in(e, in, nIn))) return rc;
+	if ((rc = stage_out(e, nOut))) return rc;
+	if ((rc = process_impl(e, e->dIn, nIn, (long long)e->cfg.C * nIn, nIn, e->dOut, nOut, (long long)e->cfg.C * nOut, nOut))) return rc;
+	return fetch_out(e, out, nOut);
+}
+int b200s_flush(b200s_engine *e, float *out, int nOut, float rate) {
+	NEED_CFG();
+	if (nOut < 0) return B200S_EINVAL;
+	int rc;
+	if ((rc = stage_out(e, nOut))) return rc;
+	if ((rc = flush_impl(e, e->dOut, nOut, (long long)e->cfg.C * nOut, nOut, rate))) return rc;
+	return fetch_out(e, out, nOut);
+}
+int b200s_output_seek(b200s_engine *e, const float *in, int inputLength) {
+	NEED_CFG();
+	if (inputLength < 0) return B200S_EINVAL;
+	int rc;
+	if ((rc = check_formant_support(e))) return rc;
+	if ((rc = stage_in(e, in, inputLength))) return rc;
+	if ((rc = output_seek_impl(e, e->dIn, inputLength, (long long)e->cfg.C * inputLength, inputLength))) return rc;
+	CK(cudaStreamSynchronize(e->stream));
+	return 0;
+}
+int b200s_exact(b200s_engine *e, const float *in, int nIn, float *out, int nOut, int *ok) { // :467-491
+	NEED_CFG();
+	if (nIn < 0 || nOut <= 0) return B200S_EINVAL;
+	int rc;
+	if ((rc = check_formant_support(e))) return rc;
+	const Cfg &g = e->cfg;
+	float playbackRate = nIn / float(nOut);
+	int seekLen = b200s_output_seek_length(e, playbackRate);
+	if (ok) *ok = 0;
+	if (nIn < seekLen) {
+		memset(out, 0, sizeof(float) * (size_t)g.S * g.C * nOut);
+		return 0;
+	}
+	if ((rc = stage_in(e, in, nIn))) return rc;
+	if ((rc = stage_out(e, nOut))) return rc;
+	const long long inSS = (long long)g.C * nIn, outSS = (long long)g.C * nOut;
+	if ((rc = output_seek_impl(e, e->dIn, nIn, inSS, seekLen))) return rc;
+	int outputIndex = int(nOut - seekLen / playbackRate); // :484
+	if ((rc = process_impl(e, e->dIn + seekLen, nIn, inSS, nIn - seekLen, e->dOut, nOut, outSS, outputIndex))) return rc;
+	if ((rc = flush_impl(e, e->dOut + outputIndex, nOut, outSS, nOut - outputIndex, playbackRate))) return rc;
+	if (ok) *ok = 1;
+	return fetch_out(e, out, nOut);
+}
+
+int b200s_timer_start(b200s_engine *e) {
+	if (!e) return B200S_EINVAL;
+	CK(cudaEventRecord(e->evStart, e->stream));
+	return 0;
+}
+int b200s_timer_stop(b200s_engine *e, float *ms) {
+	if (!e || !ms) return B200S_EINVAL;
+	CK(cudaEventRecord(e->evStop, e->stream));
+	CK(cudaEventSynchronize(e->evStop));
+	CK(cudaEventElapsedTime(ms, e->evStart, e->evStop));
+	return 0;
+}
+long long b200s_kernel_launches(const b200s_engine *e) { return e ? e->launches : 0; }
+
+// ---- white-box state ----
+static int state_desc(const b200s_engine *e, int what, float **ptr, size_t *perStream) {
+	const Cfg &g = e->cfg;
+	switch (what) {
+	case 0: *ptr = (float *)e->dStIn; *perStream = (size_t)2 * g.C * g.K; return 0;
+	case 1: *ptr = (float *)e->dStPrev; *perStream = (size_t)2 * g.C * g.K; return 0;
+	case 2: *ptr = (float *)e->dStOut; *perStream = (size_t)2 * g.C * g.K; return 0;
+	case 4: *ptr = e->dStPredE; *perStream = (size_t)g.C * g.K; return 0;
+	case 20: *ptr = e->dHist[e->histCur]; *perStream = (size_t)g.C * g.histLen; return 0;
+	case 21: *ptr = e->dPend; *perStream = (size_t)g.C * g.pendLen; return 0;
+	case 22: *ptr = e->dPendWp; *perStream = (size_t)g.C * g.pendLen; return 0;
+	}
+	return B200S_EINVAL;
+}
+int b200s_state_size(const b200s_engine *e, int what) {
+	if (!e || !e->configured) return B200S_EINVAL;
+	float *p;
+	size_t n;
+	if (state_desc(e, what, &p, &n)) return B200S_EINVAL;
+	return (int)n;
+}
+int b200s_get_state(b200s_engine *e, int what, float *dst) {
+	NEED_CFG();
+	float *p;
+	size_t n;
+	if (state_desc(e, what, &p, &n)) return B200S_EINVAL;
+	CK(cudaStreamSynchronize(e->stream));
+	CK(cudaMemcpy(dst, p, sizeof(float) * n * e->S, cudaMemcpyDeviceToHost));
+	return 0;
+}
+int b200s_set_state(b200s_engine *e, int what, const float *src) {
+	NEED_CFG();
+	float *p;
+	size_t n;
+	if (state_desc(e, what, &p, &n)) return B200S_EINVAL;
+	CK(cudaStreamSynchronize(e->stream));
+	CK(cudaMemcpy(p, src, sizeof(float) * n * e->S, cudaMemcpyHostToDevice));
+	return 0;
+}
+
+} // extern "C"

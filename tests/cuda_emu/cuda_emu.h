@@ -1,0 +1,171 @@
+// tests/cuda_emu/cuda_emu.h -- TEST INFRASTRUCTURE ONLY.
+//
+// A minimal "CUDA on CPU" shim: one OS thread per CUDA thread, one block at a time, barriers for
+// __syncthreads / warp shuffles.  It exists because the build container has no GPU: it lets the
+// `-m "not gpu"` tests execute the SAME kernel sources (signalsmith_stretch_b200/csrc/*.cu*)
+// and check their logic against the oracle before they ever reach a B200.  It is compiled only by
+// tests/cuda_emu/build.sh into tests/cuda_emu/_build/, is never shipped, and the product package
+// cannot load it (signalsmith_stretch_b200 only loads the nvcc-built library).  Not a fallback.
+#pragma once
+#include <pthread.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define B200S_SHARED static
+#define B200S_DYN_SHARED
+
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+	unsigned x, y, z;
+	dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+
+static thread_local uint3 threadIdx, blockIdx;
+static thread_local dim3 blockDim, gridDim;
+alignas(16) static float4 dyn_smem[(232 * 1024) / 16];
+
+using std::max;
+using std::min;
+
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+template <typename T>
+static inline T __ldg(const T *p) { return *p; }
+
+namespace emu {
+struct BlockCtx {
+	pthread_barrier_t blockBar;
+	std::vector<pthread_barrier_t> warpBar;
+	std::vector<uint32_t> shfl; // one slot per thread
+};
+static BlockCtx *g_ctx = nullptr;
+static thread_local int t_tid = 0;
+
+static inline void warp_barrier() { pthread_barrier_wait(&g_ctx->warpBar[t_tid >> 5]); }
+template <typename T>
+static inline T shfl_from(T v, int srcLane) {
+	static_assert(sizeof(T) == 4, "32-bit shuffles only");
+	uint32_t bits;
+	memcpy(&bits, &v, 4);
+	g_ctx->shfl[t_tid] = bits;
+	warp_barrier();
+	int base = t_tid & ~31, n = std::min<int>(32, (int)blockDim.x - base);
+	uint32_t r = (srcLane >= 0 && srcLane < n) ? g_ctx->shfl[base + srcLane] : bits;
+	warp_barrier();
+	T out;
+	memcpy(&out, &r, 4);
+	return out;
+}
+
+template <typename F>
+static void launch(dim3 grid, dim3 block, size_t smemBytes, F fn) {
+	(void)smemBytes;
+	const int T = (int)(block.x * block.y * block.z);
+	BlockCtx ctx;
+	pthread_barrier_init(&ctx.blockBar, nullptr, T);
+	int nw = (T + 31) / 32;
+	ctx.warpBar.resize(nw);
+	for (int w = 0; w < nw; ++w) pthread_barrier_init(&ctx.warpBar[w], nullptr, std::min(32, T - 32 * w));
+	ctx.shfl.assign(T, 0);
+	g_ctx = &ctx;
+	std::vector<std::thread> th;
+	th.reserve(T);
+	for (int t = 0; t < T; ++t) {
+		th.emplace_back([&, t]() {
+			t_tid = t;
+			threadIdx = uint3{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
+			blockDim = block;
+			gridDim = grid;
+			for (unsigned bz = 0; bz < grid.z; ++bz)
+				for (unsigned by = 0; by < grid.y; ++by)
+					for (unsigned bx = 0; bx < grid.x; ++bx) {
+						blockIdx = uint3{bx, by, bz};
+						fn();
+						pthread_barrier_wait(&g_ctx->blockBar);
+					}
+		});
+	}
+	for (auto &t : th) t.join();
+	for (int w = 0; w < nw; ++w) pthread_barrier_destroy(&ctx.warpBar[w]);
+	pthread_barrier_destroy(&ctx.blockBar);
+	g_ctx = nullptr;
+}
+} // namespace emu
+
+static inline void __syncthreads() { pthread_barrier_wait(&emu::g_ctx->blockBar); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
+template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, int d) { return emu::shfl_from(v, (emu::t_tid & 31) - d); }
+template <typename T>
+static inline T __shfl_down_sync(unsigned, T v, int d) { return emu::shfl_from(v, (emu::t_tid & 31) + d); }
+template <typename T>
+static inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl_from(v, src); }
+
+#define B200S_LAUNCH(kernel, grid, block, smem, stream, ...) \
+	emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
+
+// ---- the handful of runtime calls engine.cu makes ----
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+typedef void *cudaEvent_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaStreamNonBlocking = 1 };
+static inline const char *cudaGetErrorString(cudaError_t) { return "emulator error"; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
+static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(1, n + 64); return *p ? 0 : 1; }
+static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
+static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return 0; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, int) { *s = nullptr; return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = nullptr; return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
+
+#ifdef B200S_EMU_EXACT_FFT
+// Swap the oracle's double-precision modified real FFT into the analysis / synthesis kernels, so
+// that everything EXCEPT the FFT can be compared bit-exactly with the oracle.
+#include "../../oracle/fft_ref.h"
+static inline void emu_exact_forward(const float *xw, int B, int o, int N, float2 *spec) {
+	oracle::ModifiedRealFFT fft;
+	fft.resize(N);
+	std::vector<double> x(B);
+	std::vector<oracle::cplx> X(N / 2);
+	for (int i = 0; i < B; ++i) x[i] = xw[i];
+	fft.forward(x.data(), B, o, X.data());
+	for (int b = 0; b < N / 2; ++b) spec[b] = float2{float(X[b].real()), float(X[b].imag())};
+}
+static inline void emu_exact_inverse(const float2 *Y, int B, int o, int N, float *y) {
+	oracle::ModifiedRealFFT fft;
+	fft.resize(N);
+	std::vector<oracle::cplx> X(N / 2);
+	std::vector<double> t(B);
+	for (int b = 0; b < N / 2; ++b) X[b] = oracle::cplx(Y[b].x, Y[b].y);
+	fft.inverse(X.data(), t.data(), B, o);
+	for (int i = 0; i < B; ++i) y[i] = float(t[i]);
+}
+#endif
