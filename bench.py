@@ -1,0 +1,326 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the STFT phase-vocoder hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W          (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                   the reference's own CPU implementation
+
+Workload (BASELINE.json configs[1]): batch 1024 stereo streams per GPU, 48 kHz presetDefault,
+0.8x time-stretch (outputSamples = 0.8 * inputSamples, cmd/main.cpp:27,37 semantics), synthetic
+harmonic audio.  One STEP = one process() call over the whole batch carrying 32 blocks per stream
+(46 080 output / 57 600 input samples per channel = 0.96 s of output audio).
+Metric: audio output samples per second, counted per channel (batch * channels * outputSamples / t).
+
+* value      device-resident: inputs already in HBM, CUDA events on the engine's stream;
+* e2e        the same call through the host-buffer C ABI (b200s_process) from/to PINNED host memory,
+             host->device and device->host copies inside the timed region;
+* roofline   algorithmic bytes (129.2 B per output sample for this config)
+             over the measured device time, against MEASURED_PEAKS.json's HBM copy bandwidth;
+* cpu_baseline  the reference's own binary (oracle/_ref, kind "reference") on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SR = 48000
+CHANNELS = 2
+BATCH_PER_GPU = 1024
+BLOCKS_PER_STEP = 32
+RATIO_OUT = 0.8  # output length / input length
+# compulsory HBM traffic per block-channel for this configuration
+# (input read + history append + 2 analysis gathers + output/energy state + OLA ring + output)
+ALGO_BYTES_PER_BLOCK_CHANNEL = 186048
+METRIC = "audio output samples/sec (batched streams, per channel)"
+
+
+def workload(batch):
+    H = int(SR * 0.03)
+    n_out = BLOCKS_PER_STEP * H
+    n_in = int(round(n_out / RATIO_OUT))
+    return {"batch": batch, "channels": CHANNELS, "n_in": n_in, "n_out": n_out, "interval": H,
+            "samples_per_step": batch * CHANNELS * n_out}
+
+
+def config_dict(w, n_gpus):
+    return {"workload": "BASELINE configs[1]: batch=%d stereo 48 kHz presetDefault, 0.8x time-stretch, per GPU" % BATCH_PER_GPU,
+            "global_batch": w["batch"] * n_gpus, "batch_per_gpu": w["batch"], "channels": CHANNELS, "sample_rate": SR,
+            "preset": "presetDefault", "out_over_in": RATIO_OUT, "blocks_per_step": BLOCKS_PER_STEP,
+            "output_samples_per_step": w["n_out"], "input_samples_per_step": w["n_in"],
+            "parallelism": "streams sharded contiguously, %d rank(s), no data-path collective" % n_gpus,
+            "l2": "inputs (%.0f MB/step, 3 rotating buffers) larger than L2" % (w["batch"] * CHANNELS * w["n_in"] * 4 / 1e6)}
+
+
+def synth_input(batch, n, seed0=0):
+    """[batch][C][n] float32; cheap vectorised version of tests/signals.harmonic (seed = stream)."""
+    t = np.arange(n, dtype=np.float64) / SR
+    s = (np.arange(batch) + seed0)[:, None, None]
+    c = np.arange(CHANNELS)[None, :, None]
+    f0 = 110.0 * (1 + 0.01 * (s % 97)) * (1 + 0.05 * c)
+    ph = 2 * np.pi * f0 * t[None, None, :] + 3 * np.sin(2 * np.pi * 0.7 * t)[None, None, :]
+    x = np.zeros((batch, CHANNELS, n))
+    for k in range(6):
+        x += np.sin((k + 1) * ph) / (k + 1)
+    x *= (1 + 0.3 * np.sin(2 * np.pi * 2 * t))[None, None, :] * 0.2
+    rng = np.random.default_rng(1234 + seed0)
+    x += 0.01 * rng.standard_normal(x.shape)
+    return x.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [v.strip() for v in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU reference
+def cpu_reference_run(n_streams, seconds_per_stream, threads):
+    """The reference's own implementation of this workload on the host cores.
+    kind "reference": the shipped WASM binary translated to C (oracle/_ref/libwasm_stretch.so);
+    falls back to the oracle restatement ("port") only if that file is absent."""
+    import ctypes
+
+    from oracle import hdrref, wasmref
+
+    H = int(SR * 0.03)
+    n_out_total = int(seconds_per_stream * SR) // H * H
+    chunk = 480  # 480-sample output chunks
+    n_in_total = int(round(n_out_total / RATIO_OUT))
+    x = synth_input(n_streams, n_in_total)
+    if wasmref.available():
+        # native pthread pool, one reference instance per stream (oracle/ref_bench.c)
+        L = ctypes.CDLL(wasmref.lib_path())
+        L.refbench_run.restype = ctypes.c_double
+        L.refbench_run.argtypes = [ctypes.c_int] * 3 + [ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_float] + \
+            [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+        chk = ctypes.c_double(0)
+        dt = L.refbench_run(threads, n_streams, CHANNELS, float(SR), 0, 0.0, 0.0, n_in_total, n_out_total, chunk,
+                            x.ctypes.data, ctypes.byref(chk))
+        kind, how = "reference", "native pthread pool over the reference's shipped binary (oracle/_ref, WASM->C, gcc -O2)"
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+
+        def one(s):
+            o = hdrref.CpuStretch("orc")
+            o.presetDefault(CHANNELS, float(SR))
+            i = done = 0
+            while done < n_out_total:
+                co = min(chunk, n_out_total - done)
+                ci = int(round((done + co) / RATIO_OUT)) - i
+                o.process(x[s][:, i:i + ci], co)
+                i += ci
+                done += co
+
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(one, range(n_streams)))
+        dt = time.perf_counter() - t0
+        kind, how = "port", "oracle restatement (double-precision FFT) via ctypes threads"
+    total = n_streams * CHANNELS * n_out_total
+    return {"value": total / dt, "unit": "samples/s", "cores": threads, "kind": kind,
+            "sample": "%d streams x %.1f s stereo 48 kHz presetDefault 0.8x, 480-sample calls, %d threads, %.1f s wall; %s"
+                      % (n_streams, seconds_per_stream, threads, dt, how)}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals, t_all = [], []
+    n_streams = max(threads * 8, 64)
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = cpu_reference_run(n_streams, 5.0, threads)
+        if i >= args.warmup:
+            vals.append(r["value"])
+            t_all.append(time.perf_counter() - t0)
+    v = float(np.mean(vals))
+    w = workload(BATCH_PER_GPU)
+    r["value"] = v
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(t_all)) * 1e3,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": config_dict(w, args.gpus), "cpu_baseline": r,
+                      "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="streams per GPU (default: the BASELINE config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    from signalsmith_stretch_b200 import BatchStretch, build_library
+    from signalsmith_stretch_b200.shard import reduce_throughput, shard_range
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU path (use --impl reference for the CPU baseline)")
+    build_library()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    w = workload(args.batch)
+    lo, _hi = shard_range(args.batch * world, rank, world)  # this rank's streams of the global batch
+    eng = BatchStretch(args.batch, device=local_rank)
+    eng.presetDefault(CHANNELS, float(SR))
+    eng.reserve(w["n_in"], w["n_out"])
+
+    # three distinct input buffers (each >> L2), consecutive seconds of each stream's audio
+    x_host = synth_input(args.batch, 3 * w["n_in"], seed0=lo)
+    x_dev = [torch.from_numpy(np.ascontiguousarray(x_host[:, :, k * w["n_in"]:(k + 1) * w["n_in"]])).to(dev) for k in range(3)]
+    y_dev = torch.empty((args.batch, CHANNELS, w["n_out"]), dtype=torch.float32, device=dev)
+    x_pin = [torch.from_numpy(np.ascontiguousarray(x_host[:, :, k * w["n_in"]:(k + 1) * w["n_in"]])).pin_memory() for k in range(3)]
+    y_pin = torch.empty((args.batch, CHANNELS, w["n_out"]), dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident: warm-up, then exactly K timed steps
+    for i in range(args.warmup):
+        eng.process(x_dev[i % 3], w["n_out"], out=y_dev)
+    eng.synchronize()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = eng.kernel_launches()
+    eng.timer_start()
+    for i in range(args.steps):
+        eng.process(x_dev[i % 3], w["n_out"], out=y_dev)
+    ms = eng.timer_stop()
+    launches = eng.kernel_launches() - launches0
+    barrier()
+    clk = clocks.stop()
+    total, tmax = reduce_throughput(w["samples_per_step"] * args.steps, ms / 1e3, dist if world > 1 else None, dev)
+    value = total / tmax
+
+    # ---- end to end through the host-buffer C ABI: pinned host in, pinned host out, copies timed
+    for i in range(2):
+        eng.process_host_ptr(x_pin[i % 3].data_ptr(), w["n_in"], y_pin.data_ptr(), w["n_out"])
+    barrier()
+    t0 = time.perf_counter()
+    eng.timer_start()
+    for i in range(args.steps):
+        eng.process_host_ptr(x_pin[i % 3].data_ptr(), w["n_in"], y_pin.data_ptr(), w["n_out"])
+    ms_e2e_dev = eng.timer_stop()
+    torch.cuda.synchronize()
+    wall_e2e = time.perf_counter() - t0
+    barrier()
+    tot_e, t_e = reduce_throughput(w["samples_per_step"] * args.steps, max(wall_e2e, ms_e2e_dev / 1e3), dist if world > 1 else None, dev)
+    e2e = {"value": tot_e / t_e, "unit": "samples/s",
+           "h2d_bytes_per_step": int(x_pin[0].numel() * 4), "d2h_bytes_per_step": int(y_pin.numel() * 4),
+           "ms_per_step": t_e / args.steps * 1e3, "timed": "host wall clock around b200s_process() incl. pinned H2D + D2H"}
+
+    # ---- per-kernel device time (separate pass, CUDA events around every kernel of process())
+    eng.profile_begin()
+    nprof = min(args.steps, 4)
+    for i in range(nprof):
+        eng.process(x_dev[i % 3], w["n_out"], out=y_dev)
+    prof = eng.profile_end()
+    kern = {k: v[0] / max(v[1], 1) for k, v in prof.items()}
+    ksum = sum(kern.values())
+    dominant = max(kern, key=kern.get)
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    algo_bytes_step = ALGO_BYTES_PER_BLOCK_CHANNEL * args.batch * CHANNELS * BLOCKS_PER_STEP
+    ms_step_dev = ms / args.steps
+    achieved = algo_bytes_step / (ms_step_dev * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src,
+                "scope": "whole process() launch sequence (the path is not yet one fused kernel): "
+                         "%d algorithmic bytes per block-channel (SURVEY.md 8(d)) x %d block-channels per step / device time per step"
+                         % (ALGO_BYTES_PER_BLOCK_CHANNEL, args.batch * CHANNELS * BLOCKS_PER_STEP),
+                "kernel_ms_per_step": kern, "kernel_share": {k: v / ksum for k, v in kern.items()}, "dominant_kernel": dominant}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cpu = cpu_reference_run(max(8 * threads, 64), 5.0, threads)
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": tmax / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(w, world), "clocks": clk,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

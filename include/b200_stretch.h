@@ -102,6 +102,11 @@ int b200s_timer_start(b200s_engine *e);
 int b200s_timer_stop(b200s_engine *e, float *milliseconds); /* synchronises on the stop event */
 /* Kernels launched by this handle since creation (claim for bench.py's "gpu_launches"). */
 long long b200s_kernel_launches(const b200s_engine *e);
+/* Per-kernel device time of process(): between begin and end every kernel of the process()
+ * launch sequence is bracketed by CUDA events on the handle's stream.  `ms`/`counts` receive, in
+ * this order: plan, analyse, prep, chain, synth, commit (n >= 6). */
+int b200s_profile_begin(b200s_engine *e);
+int b200s_profile_end(b200s_engine *e, float *ms, int *counts, int n);
 
 /* ---- white-box state for teacher-forced parity tests ----
  * `what`: 0 input spectrum, 1 prevInput, 2 output (complex: 2*bands floats per stream-channel),

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "b200s_set_formant_semitones", "b200s_set_formant_base", "b200s_set_freq_map_table",
     "b200s_seek", "b200s_output_seek", "b200s_process", "b200s_flush", "b200s_exact",
     "b200s_seek_device", "b200s_process_device", "b200s_flush_device",
-    "b200s_timer_start", "b200s_timer_stop", "b200s_kernel_launches",
+    "b200s_timer_start", "b200s_timer_stop", "b200s_kernel_launches", "b200s_profile_begin", "b200s_profile_end",
     "b200s_state_size", "b200s_get_state", "b200s_set_state",
 ]
 
@@ -86,6 +86,7 @@ def _bind(lib):
         "b200s_seek_device": (ci, [vp, vp, ci, cd]), "b200s_process_device": (ci, [vp, vp, ci, vp, ci]),
         "b200s_flush_device": (ci, [vp, vp, ci, cf]),
         "b200s_timer_start": (ci, [vp]), "b200s_timer_stop": (ci, [vp, fp]), "b200s_kernel_launches": (cll, [vp]),
+        "b200s_profile_begin": (ci, [vp]), "b200s_profile_end": (ci, [vp, fp, ip, ci]),
         "b200s_state_size": (ci, [vp, ci]), "b200s_get_state": (ci, [vp, ci, vp]), "b200s_set_state": (ci, [vp, ci, vp]),
     }
     for name in ("batch", "channels", "block_samples", "interval_samples", "input_latency", "output_latency",
@@ -222,7 +223,10 @@ class BatchStretch:
 
     # ---- the hot path ----
     def _shape(self, n):
-        return (self.batch, self.channels(), n)
+        c = self.channels()
+        if c <= 0:
+            raise StretchError("engine not configured: call presetDefault / presetCheaper / configure first")
+        return (self.batch, c, n)
 
     def seek(self, inputs, playbackRate):
         if _is_torch_cuda(inputs):
@@ -294,6 +298,18 @@ class BatchStretch:
 
     def kernel_launches(self):
         return int(self._lib.b200s_kernel_launches(self._h))
+
+    KERNELS = ("plan", "analyse", "prep", "chain", "synth", "commit")
+
+    def profile_begin(self):
+        self._ck(self._lib.b200s_profile_begin(self._h))
+
+    def profile_end(self):
+        """{kernel: (total ms, launches)} for the process() calls since profile_begin()."""
+        ms = (ctypes.c_float * 6)()
+        cnt = (ctypes.c_int * 6)()
+        self._ck(self._lib.b200s_profile_end(self._h, ms, cnt, 6))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNELS)}
 
     def get_state(self, name):
         what = STATE[name]

@@ -31,6 +31,10 @@ struct b200s_engine {
 	cudaEvent_t evStart = 0, evStop = 0;
 	long long launches = 0;
 	std::string err;
+	// optional per-kernel CUDA-event timing (b200s_profile_begin/end)
+	bool profiling = false;
+	std::vector<cudaEvent_t> profEv; // pairs
+	std::vector<int> profKind;
 
 	// tables
 	float *dWindow = 0, *dWinProd = 0, *dWpReset = 0;
@@ -324,6 +328,25 @@ static int ensure_buf(b200s_engine *e, float **p, size_t *cap, size_t n, bool ze
 	return 0;
 }
 
+enum { PK_PLAN = 0, PK_ANALYSE, PK_PREP, PK_CHAIN, PK_SYNTH, PK_COMMIT, PK_COUNT };
+static int prof_mark(b200s_engine *e, int kind, bool begin) {
+	if (!e->profiling) return 0;
+	cudaEvent_t ev;
+	CK(cudaEventCreate(&ev));
+	CK(cudaEventRecord(ev, e->stream));
+	e->profEv.push_back(ev);
+	if (begin) e->profKind.push_back(kind);
+	return 0;
+}
+#define PROF(kind, stmt)                          \
+	do {                                          \
+		int _rc;                                  \
+		if ((_rc = prof_mark(e, kind, true))) return _rc;  \
+		stmt;                                     \
+		CKL();                                    \
+		if ((_rc = prof_mark(e, kind, false))) return _rc; \
+	} while (0)
+
 typedef void (*ChainKernel)(Ctx);
 template <int CT>
 static ChainKernel chain_kernel_for(int L) {
@@ -354,23 +377,17 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	x.inChanStride = inChanStride; x.inStreamStride = inStreamStride;
 	x.outChanStride = outChanStride; x.outStreamStride = outStreamStride;
 	const int F = frames_bound(g, nOut);
-	B200S_LAUNCH(k_plan, dim3(g.S), dim3(kThreads), 0, e->stream, x);
-	CKL();
+	PROF(PK_PLAN, B200S_LAUNCH(k_plan, dim3(g.S), dim3(kThreads), 0, e->stream, x));
 	if (F > 0) {
-		B200S_LAUNCH(k_analyse, dim3(2 * F, g.C, g.S), dim3(kThreads), smem_analyse(g), e->stream, x);
-		CKL();
-		B200S_LAUNCH(k_prep, dim3(F, g.S), dim3(kThreads), smem_prep(g), e->stream, x);
-		CKL();
+		PROF(PK_ANALYSE, B200S_LAUNCH(k_analyse, dim3(2 * F, g.C, g.S), dim3(kThreads), smem_analyse(g), e->stream, x));
+		PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, g.S), dim3(kThreads), smem_prep(g), e->stream, x));
 		const int warps = 4;
 		dim3 grid((g.S + warps - 1) / warps), block(32 * warps);
 		ChainKernel kc = g.C == 1 ? chain_kernel_for<1>(g.L) : chain_kernel_for<2>(g.L);
-		B200S_LAUNCH(kc, grid, block, 0, e->stream, x);
-		CKL();
+		PROF(PK_CHAIN, B200S_LAUNCH(kc, grid, block, 0, e->stream, x));
 	}
-	B200S_LAUNCH(k_synth, dim3(g.C, g.S), dim3(kThreads), smem_synth(g), e->stream, x);
-	CKL();
-	B200S_LAUNCH(k_commit, dim3(g.S), dim3(kThreads), 0, e->stream, x);
-	CKL();
+	PROF(PK_SYNTH, B200S_LAUNCH(k_synth, dim3(g.C, g.S), dim3(kThreads), smem_synth(g), e->stream, x));
+	PROF(PK_COMMIT, B200S_LAUNCH(k_commit, dim3(g.S), dim3(kThreads), 0, e->stream, x));
 	e->histCur ^= 1;
 	return 0;
 }
@@ -687,6 +704,30 @@ int b200s_timer_stop(b200s_engine *e, float *ms) {
 	return 0;
 }
 long long b200s_kernel_launches(const b200s_engine *e) { return e ? e->launches : 0; }
+int b200s_profile_begin(b200s_engine *e) {
+	if (!e) return B200S_EINVAL;
+	e->profiling = true;
+	return 0;
+}
+int b200s_profile_end(b200s_engine *e, float *ms, int *counts, int n) {
+	if (!e || !ms || !counts || n < PK_COUNT) return B200S_EINVAL;
+	e->profiling = false;
+	CK(cudaStreamSynchronize(e->stream));
+	for (int i = 0; i < n; ++i) {
+		ms[i] = 0;
+		counts[i] = 0;
+	}
+	for (size_t i = 0; i < e->profKind.size(); ++i) {
+		float t = 0;
+		CK(cudaEventElapsedTime(&t, e->profEv[2 * i], e->profEv[2 * i + 1]));
+		ms[e->profKind[i]] += t;
+		counts[e->profKind[i]] += 1;
+	}
+	for (cudaEvent_t ev : e->profEv) cudaEventDestroy(ev);
+	e->profEv.clear();
+	e->profKind.clear();
+	return 0;
+}
 
 // ---- white-box state ----
 static int state_desc(const b200s_engine *e, int what, float **ptr, size_t *perStream) {

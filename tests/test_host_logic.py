@@ -1,0 +1,213 @@
+"""CPU-only checks of the product's host logic and kernel logic.
+
+* the nvcc-built library loads here (no GPU), exports every symbol include/b200_stretch.h declares,
+  and fails loudly (no CPU fallback) when asked for an engine;
+* the SAME CUDA sources, run under the thread-per-CUDA-thread emulator (tests/cuda_emu), are
+  compared with the oracle: with the oracle's FFT swapped in, everything else (device block
+  scheduler, spectral prep, frame-wavefront phase chain, overlap-add, seek/flush/reset/outputSeek/
+  exact) must be BIT-EXACT; with the real shared-memory FFT the short-horizon error is bounded;
+* the multi-GPU sharding helper under gloo, world_size 2.
+"""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import signals
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rms(a):
+    return float(np.sqrt(np.mean(np.square(a, dtype=np.float64))))
+
+
+# ------------------------------------------------------------------ the shipped library
+def test_library_exports_every_declared_symbol(cuda_lib):
+    import signalsmith_stretch_b200 as pkg
+
+    header = open(os.path.join(ROOT, "include", "b200_stretch.h")).read()
+    declared = sorted(set(re.findall(r"\b(b200s_[a-z_]+)\s*\(", header)))
+    assert declared == sorted(pkg.ABI_SYMBOLS)
+    lib = ctypes.CDLL(cuda_lib)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_no_cpu_fallback(cuda_lib):
+    """Without a GPU the product must refuse to create an engine (not silently run on the CPU)."""
+    import torch
+
+    import signalsmith_stretch_b200 as pkg
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.StretchError, match="no usable CUDA device"):
+        pkg.BatchStretch(2)
+    with pytest.raises(pkg.StretchError, match="not found"):
+        pkg.BatchStretch(2, lib_path="/nonexistent/libb200stretch.so")
+
+
+def test_product_sources_never_touch_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "signalsmith_stretch_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle/" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+# ------------------------------------------------------------------ kernels under the emulator
+def _emu(path, batch):
+    from signalsmith_stretch_b200 import BatchStretch
+
+    return BatchStretch(batch, lib_path=path)
+
+
+def _oracle_batch(oracle_port, cfg, x, ratio, chunk):
+    outs = []
+    for s in range(x.shape[0]):
+        o = oracle_port()
+        cfg(o)
+        outs.append(signals.run_single(o, x[s], ratio, chunk))
+    return np.stack(outs)
+
+
+SMALL = [
+    ("identity", lambda o: o.configure(1, 512, 128), 1, 1.0, 1000),
+    ("radix3_K192_+5st", lambda o: (o.configure(1, 384, 96), o.setTransposeSemitones(5, 0)), 1, 1.0, 1000),
+    ("radix5_K160_-4st_tonality", lambda o: (o.configure(1, 320, 80), o.setTransposeSemitones(-4, 0.2)), 1, 1.0, 777),
+    ("stereo_0.8x", lambda o: o.configure(2, 512, 128), 2, 0.8, 640),
+    ("stereo_1.5x_+3st", lambda o: (o.configure(2, 512, 128), o.setTransposeSemitones(3, 0.25)), 2, 1.5, 900),
+    ("split_400_160", lambda o: (o.configure(1, 400, 160, True), o.setTransposeSemitones(2, 0)), 1, 1.0, 500),
+    ("formant_comp_stereo", lambda o: (o.configure(2, 512, 128), o.setTransposeSemitones(12, 0), o.setFormantFactor(1, True), o.setFormantBase(200 / 48000)), 2, 1.0, 640),
+    ("formant_+3st_1.25x", lambda o: (o.configure(1, 512, 128), o.setTransposeSemitones(-3, 0.2), o.setFormantSemitones(3, False), o.setFormantBase(300 / 48000)), 1, 1.25, 640),
+]
+
+
+@pytest.mark.parametrize("name,cfg,C,ratio,chunk", SMALL, ids=[c[0] for c in SMALL])
+def test_kernel_logic_bit_exact_vs_oracle(emu_libs, oracle_port, name, cfg, C, ratio, chunk):
+    x = signals.batch("harmonic", 2, C, 4000, 48000)
+    g = _emu(emu_libs["exact"], 2)
+    cfg(g)
+    y = signals.run_batch(g, x, ratio, chunk)
+    ref = _oracle_batch(oracle_port, cfg, x, ratio, chunk)
+    assert np.array_equal(y, ref), "max diff %g" % np.abs(y - ref).max()
+
+
+def test_api_sequence_bit_exact_vs_oracle(emu_libs, oracle_port):
+    """seek / silence bypass / flush / reset / outputSeek / exact through the batched ABI."""
+    x = signals.harmonic(6000, 48000)[None]
+
+    def seq(o, wrap, unwrap):
+        o.configure(1, 512, 128)
+        o.setTransposeSemitones(3, 0)
+        outs = []
+        o.seek(wrap(x[:, :300]), 1.0)
+        outs.append(unwrap(o.process(wrap(x[:, 300:780]), 480)))
+        z = np.zeros((1, 3000), np.float32)
+        outs.append(unwrap(o.process(wrap(z[:, :1200]), 1200)))  # counts silence
+        outs.append(unwrap(o.process(wrap(z[:, :400]), 400)))    # first bypass call: state zeroed
+        outs.append(unwrap(o.process(wrap(z[:, :400]), 500)))    # bypass, in != out
+        outs.append(unwrap(o.process(wrap(x[:, 800:1760]), 900)))
+        outs.append(unwrap(o.flush(100, 1.0)))
+        outs.append(unwrap(o.process(wrap(x[:, 2000:2480]), 480)))
+        outs.append(unwrap(o.flush(500, 1.1)))
+        o.reset()
+        outs.append(unwrap(o.process(wrap(x[:, 2000:2480]), 240)))
+        o.outputSeek(wrap(x[:, : o.outputSeekLength(1.3)]))
+        outs.append(unwrap(o.process(wrap(x[:, 500:1124]), 480)))
+        ok, e = o.exact(wrap(x[:, :4000]), 5000)
+        assert ok
+        outs.append(unwrap(e))
+        ok, e = o.exact(wrap(x[:, :100]), 5000)  # too short: zero output, false (:471-479)
+        assert not ok and not np.any(e)
+        return np.concatenate(outs, axis=1)
+
+    ref = seq(oracle_port(), lambda a: a, lambda a: a)
+    got = seq(_emu(emu_libs["exact"], 1), lambda a: a[None], lambda a: np.asarray(a)[0])
+    assert np.array_equal(ref, got), "max diff %g" % np.abs(ref - got).max()
+
+
+def test_streams_are_independent_and_chunking_is_invariant(emu_libs):
+    """A stream's output does not depend on its neighbours in the batch nor on the call chunking."""
+    x = signals.batch("harmonic", 3, 1, 3000, 48000)
+    cfg = lambda o: (o.configure(1, 384, 96), o.setTransposeSemitones(4, 0.2))  # noqa: E731
+    g3 = _emu(emu_libs["float"], 3)
+    cfg(g3)
+    y3 = signals.run_batch(g3, x, 1.0, 3000)
+    g1 = _emu(emu_libs["float"], 1)
+    cfg(g1)
+    y1 = signals.run_batch(g1, x[1:2], 1.0, 250)
+    assert np.array_equal(y3[1:2], y1)
+
+
+def test_shared_memory_fft_accuracy(emu_libs, oracle_port):
+    """Real float Stockham FFT (radix 4/2 + 3 or 5) vs the oracle's double FFT: identity config is a
+    pure delay to 1e-6 for every radix mix, presets included."""
+    for cfg, C, n in ((lambda o: o.configure(1, 384, 96), 1, 2000),      # K=192 = 3*4^3
+                      (lambda o: o.configure(1, 320, 80), 1, 2000),      # K=160 = 5*4^2*2
+                      (lambda o: o.configure(1, 256, 64), 1, 2000),      # K=128 = 4^3*2
+                      (lambda o: o.presetDefault(1, 48000.0), 1, 5760 + 1440 * 2)):  # K=3072
+        x = signals.batch("harmonic", 1, C, n, 48000)
+        g = _emu(emu_libs["float"], 1)
+        cfg(g)
+        y = signals.run_batch(g, x, 1.0, n)
+        ref = _oracle_batch(oracle_port, cfg, x, 1.0, n)
+        assert rms(y - ref) <= 1e-6
+
+
+def test_unsupported_features_fail_loudly(emu_libs):
+    from signalsmith_stretch_b200 import StretchError
+
+    g = _emu(emu_libs["float"], 1)
+    with pytest.raises(StretchError):
+        g.process(np.zeros((1, 1, 10), np.float32), 10)  # not configured
+    with pytest.raises(StretchError, match="channels"):
+        g.configure(3, 512, 128)
+    g.configure(1, 512, 128)
+    g.setFormantSemitones(3)
+    g.setFormantBase(0)  # automatic pitch detection for formants: not on the GPU path yet
+    with pytest.raises(StretchError, match="setFormantBase"):
+        g.process(np.zeros((1, 1, 10), np.float32), 10)
+
+
+# ------------------------------------------------------------------ sharding, gloo world_size 2
+def test_shard_range_partitions_the_batch():
+    from signalsmith_stretch_b200.shard import shard_range
+
+    for batch in (1, 7, 8, 1024, 8192):
+        for world in (1, 2, 3, 8):
+            cover = []
+            for r in range(world):
+                lo, hi = shard_range(batch, r, world)
+                cover += list(range(lo, hi))
+            assert cover == list(range(batch))
+
+
+def test_gloo_two_ranks_reduce_the_throughput_counter():
+    script = r"""
+import os, sys
+sys.path.insert(0, %r)
+import torch.distributed as dist
+from signalsmith_stretch_b200.shard import shard_range, reduce_throughput
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"], rank=int(os.environ["RANK"]), world_size=2)
+lo, hi = shard_range(9, dist.get_rank(), 2)
+total, tmax = reduce_throughput((hi - lo) * 1000, 1.0 + dist.get_rank(), dist)
+assert total == 9000 and tmax == 2.0, (total, tmax)
+dist.destroy_process_group()
+print("ok")
+""" % ROOT
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = [subprocess.Popen([sys.executable, "-c", script], env=dict(os.environ, RANK=str(r), PORT=str(port)),
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    for p in procs:
+        out, err = p.communicate(timeout=120)
+        assert p.returncode == 0 and "ok" in out, err
