@@ -144,7 +144,42 @@ static double bessel0(double x) {
 static const int kThreads = 256;
 static size_t smem_analyse(const Cfg &g) { return sizeof(float2) * 2 * g.K; }
 static size_t smem_prep(const Cfg &g) { return sizeof(float) * (7 * (size_t)g.K + 8); }
+static size_t smem_chain(const Cfg &g, int warps) { return (g.C == 1 ? sizeof(ChainTiles<1>) : sizeof(ChainTiles<2>)) * warps; }
 static size_t smem_synth(const Cfg &g) { return sizeof(float2) * 2 * g.K + sizeof(float) * 2 * g.pendLen; }
+
+enum { PK_PLAN = 0, PK_ANALYSE, PK_PREP, PK_CHAIN, PK_SYNTH, PK_COMMIT, PK_COUNT };
+static int prof_mark(b200s_engine *e, int kind, bool begin) {
+	if (!e->profiling) return 0;
+	cudaEvent_t ev;
+	CK(cudaEventCreate(&ev));
+	CK(cudaEventRecord(ev, e->stream));
+	e->profEv.push_back(ev);
+	if (begin) e->profKind.push_back(kind);
+	return 0;
+}
+#define PROF(kind, stmt)                          \
+	do {                                          \
+		int _rc;                                  \
+		if ((_rc = prof_mark(e, kind, true))) return _rc;  \
+		stmt;                                     \
+		CKL();                                    \
+		if ((_rc = prof_mark(e, kind, false))) return _rc; \
+	} while (0)
+
+typedef void (*ChainKernel)(Ctx);
+template <int CT>
+static ChainKernel chain_kernel_for(int L) {
+	switch (L) {
+	case 1: return k_chain<CT, 1>;
+	case 2: return k_chain<CT, 2>;
+	case 3: return k_chain<CT, 3>;
+	case 4: return k_chain<CT, 4>;
+	case 5: return k_chain<CT, 5>;
+	case 6: return k_chain<CT, 6>;
+	case 7: return k_chain<CT, 7>;
+	default: return k_chain<CT, 8>;
+	}
+}
 
 static int reset_impl(b200s_engine *e, bool full) {
 	Ctx x = make_ctx(e);
@@ -293,6 +328,7 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	CK(cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep(g)));
 	CK(cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_synth(g)));
 	CK(cudaFuncSetAttribute(k_flush_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * g.B)));
+	CK(cudaFuncSetAttribute(g.C == 1 ? chain_kernel_for<1>(g.L) : chain_kernel_for<2>(g.L), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, 4)));
 #endif
 	e->configured = true;
 	return reset_impl(e, true);
@@ -328,40 +364,6 @@ static int ensure_buf(b200s_engine *e, float **p, size_t *cap, size_t n, bool ze
 	return 0;
 }
 
-enum { PK_PLAN = 0, PK_ANALYSE, PK_PREP, PK_CHAIN, PK_SYNTH, PK_COMMIT, PK_COUNT };
-static int prof_mark(b200s_engine *e, int kind, bool begin) {
-	if (!e->profiling) return 0;
-	cudaEvent_t ev;
-	CK(cudaEventCreate(&ev));
-	CK(cudaEventRecord(ev, e->stream));
-	e->profEv.push_back(ev);
-	if (begin) e->profKind.push_back(kind);
-	return 0;
-}
-#define PROF(kind, stmt)                          \
-	do {                                          \
-		int _rc;                                  \
-		if ((_rc = prof_mark(e, kind, true))) return _rc;  \
-		stmt;                                     \
-		CKL();                                    \
-		if ((_rc = prof_mark(e, kind, false))) return _rc; \
-	} while (0)
-
-typedef void (*ChainKernel)(Ctx);
-template <int CT>
-static ChainKernel chain_kernel_for(int L) {
-	switch (L) {
-	case 1: return k_chain<CT, 1>;
-	case 2: return k_chain<CT, 2>;
-	case 3: return k_chain<CT, 3>;
-	case 4: return k_chain<CT, 4>;
-	case 5: return k_chain<CT, 5>;
-	case 6: return k_chain<CT, 6>;
-	case 7: return k_chain<CT, 7>;
-	default: return k_chain<CT, 8>;
-	}
-}
-
 // process() on device buffers with explicit strides (floats between channels / streams)
 static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, long long inStreamStride, int nIn,
                         float *dOut, int outChanStride, long long outStreamStride, int nOut) {
@@ -384,7 +386,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 		const int warps = 4;
 		dim3 grid((g.S + warps - 1) / warps), block(32 * warps);
 		ChainKernel kc = g.C == 1 ? chain_kernel_for<1>(g.L) : chain_kernel_for<2>(g.L);
-		PROF(PK_CHAIN, B200S_LAUNCH(kc, grid, block, 0, e->stream, x));
+		PROF(PK_CHAIN, B200S_LAUNCH(kc, grid, block, smem_chain(g, warps), e->stream, x));
 	}
 	PROF(PK_SYNTH, B200S_LAUNCH(k_synth, dim3(g.C, g.S), dim3(kThreads), smem_synth(g), e->stream, x));
 	PROF(PK_COMMIT, B200S_LAUNCH(k_commit, dim3(g.S), dim3(kThreads), 0, e->stream, x));
