@@ -142,10 +142,10 @@ static double bessel0(double x) {
 }
 
 static const int kThreads = 256;
-static size_t smem_analyse(const Cfg &g) { return sizeof(float2) * 2 * g.K; }
+static size_t smem_analyse(const Cfg &g) { return sizeof(float2) * 2 * fft_buf_len(g.K); }
 static size_t smem_prep(const Cfg &g) { return sizeof(float) * (7 * (size_t)g.K + 8); }
 static size_t smem_chain(const Cfg &g, int warps) { return (g.C == 1 ? sizeof(ChainTiles<1>) : sizeof(ChainTiles<2>)) * warps; }
-static size_t smem_synth(const Cfg &g) { return sizeof(float2) * 2 * g.K + sizeof(float) * 2 * g.pendLen; }
+static size_t smem_synth(const Cfg &g) { return sizeof(float2) * 2 * fft_buf_len(g.K) + sizeof(float) * 2 * g.pendLen; }
 
 enum { PK_PLAN = 0, PK_ANALYSE, PK_PREP, PK_CHAIN, PK_SYNTH, PK_COMMIT, PK_COUNT };
 static int prof_mark(b200s_engine *e, int kind, bool begin) {
@@ -210,16 +210,25 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	g.pendLen = g.B + (g.split ? g.H : 0);
 	g.addOff = g.split ? g.H : 0;
 	g.o = g.B / 2;
-	{ // Stockham plan: radix 4s, one radix 2 if needed, the odd radix last
-		int k = g.K, odd = 1;
+	{ // Stockham plan: power-of-two radices first (16s, then 8/4/2), the radix carrying the odd factor last
+		int k = g.K, odd = 1, n = 0;
 		if (k % 3 == 0) { odd = 3; k /= 3; }
 		else if (k % 5 == 0) { odd = 5; k /= 5; }
-		int n = 0;
-		while (k % 4 == 0) { g.radix[n++] = 4; k /= 4; }
-		if (k % 2 == 0) { g.radix[n++] = 2; k /= 2; }
-		if (k != 1) { e->err = "unsupported FFT size"; return B200S_EUNSUPPORTED; }
-		if (odd > 1) g.radix[n++] = odd;
+		int last = odd;
+		if (odd == 3) { int c = 0; while (c < 2 && k % 2 == 0 && k > 1) { last *= 2; k /= 2; ++c; } } // 12, 6 or 3
+		if (odd == 5) { if (k % 2 == 0 && k > 1) { last *= 2; k /= 2; } }                            // 10 or 5
+		if (k & (k - 1)) { e->err = "unsupported FFT size"; return B200S_EUNSUPPORTED; }
+		while (k % 16 == 0 && k > 16) { g.radix[n++] = 16; k /= 16; }
+		if (k == 16 && last > 1) { g.radix[n++] = 16; k = 1; }
+		else if (k == 16) { g.radix[n++] = 4; last = 4; k = 1; }
+		if (k == 8) { g.radix[n++] = 8; k = 1; }
+		if (k == 4) { g.radix[n++] = 4; k = 1; }
+		if (k == 2) { g.radix[n++] = 2; k = 1; }
+		if (last > 1) g.radix[n++] = last;
 		g.nStages = n;
+		int prod = 1;
+		for (int i = 0; i < n; ++i) prod *= g.radix[i];
+		if (prod != g.K) { e->err = "internal: FFT plan does not factor the size"; return B200S_EUNSUPPORTED; }
 	}
 	if (g.L < 1 || g.L > 8 || (channels > 2)) {
 		e->err = "GPU path supports 1-2 channels and block/interval ratios with round(fftSamples/interval) in 1..8";
@@ -382,7 +391,10 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	PROF(PK_PLAN, B200S_LAUNCH(k_plan, dim3(g.S), dim3(kThreads), 0, e->stream, x));
 	if (F > 0) {
 		PROF(PK_ANALYSE, B200S_LAUNCH(k_analyse, dim3(2 * F, g.C, g.S), dim3(kThreads), smem_analyse(g), e->stream, x));
-		PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, g.S), dim3(kThreads), smem_prep(g), e->stream, x));
+		// unmapped, formant-free calls (pure time-stretch) use none of k_prep's shared arrays except
+		// the identity map: a small launch footprint lifts its occupancy
+		const bool plain = !(e->prm.mapN > 0 || e->prm.freqMultiplier != 1.0f) && e->prm.formantMultiplier == 1.0f;
+		PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, g.S), dim3(kThreads), plain ? 64 : smem_prep(g), e->stream, x));
 		const int warps = 4;
 		dim3 grid((g.S + warps - 1) / warps), block(32 * warps);
 		ChainKernel kc = g.C == 1 ? chain_kernel_for<1>(g.L) : chain_kernel_for<2>(g.L);
