@@ -182,6 +182,18 @@ class CpuStretch:
             return v.reshape(K, 2)
         return v
 
+    def signal_state(self):
+        """(oracle restatement only) the buffers the CUDA engine also keeps, for teacher-forced tests."""
+        K, C = self.bands(), self.channels
+        out = {}
+        for name, what in (("history", 20), ("pending", 21), ("pendingWp", 22)):
+            buf = np.zeros(C * (self.blockSamples() + 2 * self.intervalSamples()) + 16, np.float32)
+            n = self.f["get_state"](self.h, what, _fp(buf))
+            out[name] = buf[:n].reshape(C, -1).copy()
+        for name in ("input", "prevInput", "output", "predEnergy"):
+            out[name] = self.state(name)
+        return out
+
     def peaks(self):
         n = self.f["num_peaks"](self.h)
         buf = np.zeros(2 * n + 2, np.float32)

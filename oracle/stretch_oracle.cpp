@@ -830,9 +830,22 @@ int orc_get_state(void *h, int what, float *dst) {
 	}
 	case 10: putc(s.predInput); break;
 	case 11: for (float v : s.formantMetric) dst[n++] = v; break;
+	// 20..22: the linear signal buffers, same layout as the CUDA engine's state (teacher forcing)
+	case 20: for (float v : s.hist) dst[n++] = v; break;
+	case 21: for (float v : s.pend) dst[n++] = v; break;
+	case 22: for (int c = 0; c < C; ++c) for (float v : s.pendWp) dst[n++] = v; break;
 	default: return -1;
 	}
 	return n;
+}
+int orc_state_size(void *h, int what) {
+	Stretch &s = *(Stretch *)h;
+	switch (what) {
+	case 20: return s.C * s.histLen;
+	case 21: return s.C * s.pendLen;
+	case 22: return s.C * s.pendLen;
+	}
+	return -1;
 }
 int orc_num_peaks(void *h) { return (int)((Stretch *)h)->peakIn.size(); }
 int orc_get_peaks(void *h, float *dst) {

@@ -96,6 +96,7 @@ struct Ctx {
 	// tables
 	const float *window, *winProd, *wpReset;
 	const float2 *rot, *twiddle, *pretw;
+	float2 rot0, rotStep; // rot[b+1] = rot[b] * rotStep in float, the reference's own recurrence (:647-655)
 	// state
 	Sched *sched;
 	float *histCur, *histNext;

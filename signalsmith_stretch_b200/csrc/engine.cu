@@ -15,6 +15,7 @@
 
 #include "../../include/b200_stretch.h"
 #include "kernels.cuh"
+#include "chain_direct.cuh"
 
 using namespace b200s;
 
@@ -39,6 +40,7 @@ struct b200s_engine {
 	// tables
 	float *dWindow = 0, *dWinProd = 0, *dWpReset = 0;
 	float2 *dRot = 0, *dTwiddle = 0, *dPretw = 0;
+	float2 rot0, rotStep;
 	float *dMapIn = 0, *dMapOut = 0;
 	// state
 	Sched *dSched = 0;
@@ -112,6 +114,7 @@ static Ctx make_ctx(b200s_engine *e) {
 	x.prm.mapOut = e->dMapOut;
 	x.window = e->dWindow; x.winProd = e->dWinProd; x.wpReset = e->dWpReset;
 	x.rot = e->dRot; x.twiddle = e->dTwiddle; x.pretw = e->dPretw;
+	x.rot0 = e->rot0; x.rotStep = e->rotStep;
 	x.sched = e->dSched;
 	x.histCur = e->dHist[e->histCur]; x.histNext = e->dHist[e->histCur ^ 1];
 	x.pend = e->dPend; x.pendWp = e->dPendWp;
@@ -144,7 +147,6 @@ static double bessel0(double x) {
 static const int kThreads = 256;
 static size_t smem_analyse(const Cfg &g) { return sizeof(float2) * 2 * fft_buf_len(g.K); }
 static size_t smem_prep(const Cfg &g) { return sizeof(float) * (7 * (size_t)g.K + 8); }
-static size_t smem_chain(const Cfg &g, int warps) { return (g.C == 1 ? sizeof(ChainTiles<1>) : sizeof(ChainTiles<2>)) * warps; }
 static size_t smem_synth(const Cfg &g) { return sizeof(float2) * 2 * fft_buf_len(g.K) + sizeof(float) * 2 * g.pendLen; }
 
 enum { PK_PLAN = 0, PK_ANALYSE, PK_PREP, PK_CHAIN, PK_SYNTH, PK_COMMIT, PK_COUNT };
@@ -168,17 +170,25 @@ static int prof_mark(b200s_engine *e, int kind, bool begin) {
 
 typedef void (*ChainKernel)(Ctx);
 template <int CT>
-static ChainKernel chain_kernel_for(int L) {
+static ChainKernel chain_kernel_for(int L, bool direct) {
 	switch (L) {
-	case 1: return k_chain<CT, 1>;
-	case 2: return k_chain<CT, 2>;
-	case 3: return k_chain<CT, 3>;
-	case 4: return k_chain<CT, 4>;
-	case 5: return k_chain<CT, 5>;
-	case 6: return k_chain<CT, 6>;
-	case 7: return k_chain<CT, 7>;
-	default: return k_chain<CT, 8>;
+	case 1: return direct ? k_chain_direct<CT, 1> : k_chain<CT, 1, false>;
+	case 2: return direct ? k_chain_direct<CT, 2> : k_chain<CT, 2, false>;
+	case 3: return direct ? k_chain_direct<CT, 3> : k_chain<CT, 3, false>;
+	case 4: return direct ? k_chain_direct<CT, 4> : k_chain<CT, 4, false>;
+	case 5: return direct ? k_chain_direct<CT, 5> : k_chain<CT, 5, false>;
+	case 6: return direct ? k_chain_direct<CT, 6> : k_chain<CT, 6, false>;
+	case 7: return direct ? k_chain_direct<CT, 7> : k_chain<CT, 7, false>;
+	default: return direct ? k_chain_direct<CT, 8> : k_chain<CT, 8, false>;
 	}
+}
+static ChainKernel chain_kernel(const Cfg &g, bool direct) {
+	return g.C == 1 ? chain_kernel_for<1>(g.L, direct) : chain_kernel_for<2>(g.L, direct);
+}
+static const int kChainWarps = 1; // one stream per CTA: 1024 streams spread evenly over the 148 SMs
+static size_t smem_chain(const Cfg &g, bool direct) {
+	size_t per = direct ? (g.C == 1 ? sizeof(DirectTiles2<1>) : sizeof(DirectTiles2<2>)) : (g.C == 1 ? sizeof(ChainTiles<1>) : sizeof(ChainTiles<2>));
+	return per * kChainWarps;
 }
 
 static int reset_impl(b200s_engine *e, bool full) {
@@ -282,6 +292,8 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 		std::complex<float> r = std::polar(1.0f, b2f(0) * float(g.H) * float(2 * M_PI));
 		float freqStep = b2f(1) - b2f(0);
 		std::complex<float> step = std::polar(1.0f, freqStep * float(g.H) * float(2 * M_PI));
+		e->rot0 = make_float2(r.real(), r.imag());
+		e->rotStep = make_float2(step.real(), step.imag());
 		for (int b = 0; b < g.K; ++b) {
 			rot[b] = make_float2(r.real(), r.imag());
 			r = std::complex<float>(r.real() * step.real() - r.imag() * step.imag(), r.real() * step.imag() + r.imag() * step.real());
@@ -337,7 +349,8 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	CK(cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep(g)));
 	CK(cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_synth(g)));
 	CK(cudaFuncSetAttribute(k_flush_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * g.B)));
-	CK(cudaFuncSetAttribute(g.C == 1 ? chain_kernel_for<1>(g.L) : chain_kernel_for<2>(g.L), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, 4)));
+	CK(cudaFuncSetAttribute(chain_kernel(g, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, false)));
+	CK(cudaFuncSetAttribute(chain_kernel(g, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, true)));
 #endif
 	e->configured = true;
 	return reset_impl(e, true);
@@ -391,14 +404,13 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	PROF(PK_PLAN, B200S_LAUNCH(k_plan, dim3(g.S), dim3(kThreads), 0, e->stream, x));
 	if (F > 0) {
 		PROF(PK_ANALYSE, B200S_LAUNCH(k_analyse, dim3(2 * F, g.C, g.S), dim3(kThreads), smem_analyse(g), e->stream, x));
-		// unmapped, formant-free calls (pure time-stretch) use none of k_prep's shared arrays except
-		// the identity map: a small launch footprint lifts its occupancy
+		// Pure time-stretch (no frequency map, no formants): the chain forms its terms directly from
+		// the spectra and k_prep is skipped; otherwise k_prep produces the coefficient arrays.
 		const bool plain = !(e->prm.mapN > 0 || e->prm.freqMultiplier != 1.0f) && e->prm.formantMultiplier == 1.0f;
-		PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, g.S), dim3(kThreads), plain ? 64 : smem_prep(g), e->stream, x));
-		const int warps = 4;
-		dim3 grid((g.S + warps - 1) / warps), block(32 * warps);
-		ChainKernel kc = g.C == 1 ? chain_kernel_for<1>(g.L) : chain_kernel_for<2>(g.L);
-		PROF(PK_CHAIN, B200S_LAUNCH(kc, grid, block, smem_chain(g, warps), e->stream, x));
+		if (!plain) PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, g.S), dim3(kThreads), smem_prep(g), e->stream, x));
+		dim3 grid((g.S + kChainWarps - 1) / kChainWarps), block(32 * kChainWarps);
+		ChainKernel kc = chain_kernel(g, plain);
+		PROF(PK_CHAIN, B200S_LAUNCH(kc, grid, block, smem_chain(g, plain), e->stream, x));
 	}
 	PROF(PK_SYNTH, B200S_LAUNCH(k_synth, dim3(g.C, g.S), dim3(kThreads), smem_synth(g), e->stream, x));
 	PROF(PK_COMMIT, B200S_LAUNCH(k_commit, dim3(g.S), dim3(kThreads), 0, e->stream, x));

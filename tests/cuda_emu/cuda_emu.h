@@ -22,6 +22,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __launch_bounds__(...)
 #define B200S_SHARED static
 #define B200S_DYN_SHARED
 
