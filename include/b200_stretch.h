@@ -108,6 +108,10 @@ long long b200s_kernel_launches(const b200s_engine *e);
 int b200s_profile_begin(b200s_engine *e);
 int b200s_profile_end(b200s_engine *e, float *ms, int *counts, int n);
 
+/* Device self-test: the branch-free division / square root of the phase chain against the IEEE
+ * round-to-nearest intrinsics on `n` pseudo-random operand pairs; returns the mismatch counts. */
+int b200s_selftest_divsqrt(b200s_engine *e, long long n, long long seed, long long *div_mismatch, long long *sqrt_mismatch);
+
 /* ---- white-box state for teacher-forced parity tests ----
  * `what`: 0 input spectrum, 1 prevInput, 2 output (complex: 2*bands floats per stream-channel),
  *         4 prediction energy (bands floats per stream-channel),

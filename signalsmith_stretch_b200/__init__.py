@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "b200s_seek", "b200s_output_seek", "b200s_process", "b200s_flush", "b200s_exact",
     "b200s_seek_device", "b200s_process_device", "b200s_flush_device",
     "b200s_timer_start", "b200s_timer_stop", "b200s_kernel_launches", "b200s_profile_begin", "b200s_profile_end",
+    "b200s_selftest_divsqrt",
     "b200s_state_size", "b200s_get_state", "b200s_set_state",
 ]
 
@@ -87,6 +88,7 @@ def _bind(lib):
         "b200s_flush_device": (ci, [vp, vp, ci, cf]),
         "b200s_timer_start": (ci, [vp]), "b200s_timer_stop": (ci, [vp, fp]), "b200s_kernel_launches": (cll, [vp]),
         "b200s_profile_begin": (ci, [vp]), "b200s_profile_end": (ci, [vp, fp, ip, ci]),
+        "b200s_selftest_divsqrt": (ci, [vp, cll, cll, ctypes.POINTER(cll), ctypes.POINTER(cll)]),
         "b200s_state_size": (ci, [vp, ci]), "b200s_get_state": (ci, [vp, ci, vp]), "b200s_set_state": (ci, [vp, ci, vp]),
     }
     for name in ("batch", "channels", "block_samples", "interval_samples", "input_latency", "output_latency",
@@ -310,6 +312,11 @@ class BatchStretch:
         cnt = (ctypes.c_int * 6)()
         self._ck(self._lib.b200s_profile_end(self._h, ms, cnt, 6))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNELS)}
+
+    def selftest_divsqrt(self, n=1 << 27, seed=1):
+        a, b = ctypes.c_longlong(0), ctypes.c_longlong(0)
+        self._ck(self._lib.b200s_selftest_divsqrt(self._h, n, seed, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
 
     def get_state(self, name):
         what = STATE[name]

@@ -12,6 +12,8 @@
 //   * row pointers of the 32 blocks live in shared memory, so the cp.async fill and the write-back
 //     of a chunk are a handful of predicated instructions per lane.
 #pragma once
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace b200s {
@@ -54,7 +56,9 @@ __global__ void __launch_bounds__(32) k_chain_direct(Ctx x) {
 		const bool carryE = active && (lane == 31 || f == cl.nFrames - 1); // Prediction::energy needed later
 		const float tf = fmaxf(fr.timeFactor, 1.0f / B200S_MAX_CLEAN_STRETCH); // :638
 		const float longTf = fmul((float)LT, tf);
-		const bool farGather = longTf > (float)(CHAIN_RING - CHAIN_CH - 3); // > 2x stretch: outside the window
+		// stretch beyond 2x: the interpolation points fall outside the staged window; the whole warp then
+		// takes the slow variant of the step (gathers from HBM)
+		const bool farAny = __any_sync(0xffffffffu, active && longTf > (float)(CHAIN_RING - CHAIN_CH - 3));
 		const float2 *prevOut[CT];
 		const float *prevE[CT];
 		const float2 *myIn[CT];
@@ -85,7 +89,10 @@ __global__ void __launch_bounds__(32) k_chain_direct(Ctx x) {
 			t1P[c] = lastFinal[c] = make_float2(0.f, 0.f);
 			lastE[c] = 0.f;
 		}
-		float2 rotq = rot0; // rot[q] for this lane's current q (valid once q >= 0)
+		// rot[q] for this lane's current q (valid once q >= 0); blocks without a new spectrum are not
+		// rotated (:642): multiplying by 1+0i is exact, so they just carry the identity
+		float2 rotq = rotOn ? rot0 : make_float2(1.f, 0.f);
+		const float2 rotS = rotOn ? rotStep : make_float2(1.f, 0.f);
 		const int steps = K + LT + D * (nAct - 1);
 		for (int k0 = 0; k0 < steps; k0 += CHAIN_CH) {
 			// ---------------- stage the chunk: 8 new bins per block ----------------
@@ -110,9 +117,9 @@ __global__ void __launch_bounds__(32) k_chain_direct(Ctx x) {
 			}
 			cp_async_wait_all();
 			__syncwarp();
-			// ---------------- CHAIN_CH steps, fully unrolled ----------------
-#pragma unroll
-			for (int i = 0; i < CHAIN_CH; ++i) {
+			// ---------------- CHAIN_CH steps ----------------
+			auto step = [&](const int i, auto farTag) {
+				constexpr bool FAR = decltype(farTag)::value;
 				const int q = k0 + i - D * lane;
 				const int b = q - LT;
 				const bool qIn = active && (unsigned)q < (unsigned)K;
@@ -133,39 +140,42 @@ __global__ void __launch_bounds__(32) k_chain_direct(Ctx x) {
 					ro.x = __shfl_up_sync(0xffffffffu, lastFinal[c].x, 1);
 					ro.y = __shfl_up_sync(0xffffffffu, lastFinal[c].y, 1);
 					float re = __shfl_up_sync(0xffffffffu, lastE[c], 1);
-					if (lane == 0) {
-						ro = U.p0Out[c][i];
-						re = U.p0E[c][i];
+					{
+						const float2 p0 = U.p0Out[c][i];
+						const float p0e = U.p0E[c][i];
+						ro = make_float2(lane == 0 ? p0.x : ro.x, lane == 0 ? p0.y : ro.y);
+						re = lane == 0 ? p0e : re;
 					}
 					const float2 inq = U.in[c][q & (CHAIN_RING - 1)][lane];
 					float2 pv = U.pv[c][i][lane];
 					float2 lo2, hi2, lo1, hi1;
-					if (!farGather) {
+					if constexpr (!FAR) {
 						lo2 = sel2(l2 >= 0, U.in[c][l2 & (CHAIN_RING - 1)][lane]);
 						hi2 = sel2(l2 >= -1, U.in[c][(l2 + 1) & (CHAIN_RING - 1)][lane]);
 						lo1 = sel2(l1 >= 0, U.in[c][l1 & (CHAIN_RING - 1)][lane]);
 						hi1 = sel2(l1 >= -1, U.in[c][(l1 + 1) & (CHAIN_RING - 1)][lane]);
-					} else { // extreme stretch: gather straight from the spectrum row
+					} else { // extreme stretch (> 2x): gather straight from the spectrum row
 						lo2 = spec_at(myIn[c], l2, K);
 						hi2 = spec_at(myIn[c], l2 + 1, K);
 						lo1 = spec_at(myIn[c], l1, K);
 						hi1 = spec_at(myIn[c], l1 + 1, K);
 					}
-					if (rotOn) { // :653-654 rotate Band::output and Band::prevInput by one interval
-						pv = xmul(pv, rotq);
-						ro = xmul(ro, rotq);
-					}
+					pv = xmul(pv, rotq); // :653-654 rotate Band::output and Band::prevInput by one interval
+					ro = xmul(ro, rotq);
 					const float e = xnorm(inq);                           // :679 (identity map: energy = |input|^2)
 					const float2 phase = xmul(ro, xmulc(inq, pv));         // :714-715
 					const float den = fadd(fmaxf(re, e), B200S_NOISE_FLOOR);
-					newPre[c] = sel2(qIn, make_float2(fdiv(phase.x, den), fdiv(phase.y, den))); // :716
+					newPre[c] = sel2(qIn, make_float2(fdivq(phase.x, den), fdivq(phase.y, den))); // :716
 					newE[c] = qIn ? e : 0.f;
 					newIn[c] = sel2(qIn, inq);
 					newT2[c] = sel2(qIn, xmulc(inq, xlerp2(lo2, hi2, f2))); // long twist at q (:758)
 					// short twist at b+1 (:751,:771): Prediction::input[b+1] is inF[c][1] before the shift
 					t1N[c] = xmulc(LT > 1 ? inF[c][LT > 1 ? 1 : 0] : newIn[c], xlerp2(lo1, hi1, f1));
 				}
-				if (rotOn && q >= 0) rotq = xmul(rotq, rotStep);
+				{
+					const float2 rn = xmul(rotq, rotS);
+					rotq = make_float2(q >= 0 ? rn.x : rotq.x, q >= 0 ? rn.y : rotq.y);
+				}
 				// ---- FIFO rotation (pure renaming after unrolling): what falls out belongs to bin b
 				float eB[CT];
 				float2 t2B[CT], inB[CT];
@@ -210,13 +220,13 @@ __global__ void __launch_bounds__(32) k_chain_direct(Ctx x) {
 				phase = xadd(phase, sel2(b >= LT, xmul(ohL, t2b)));       // :761
 				phase = xadd(phase, sel2(b < K - 1, xmulc(pr1, t1n)));    // :774
 				phase = xadd(phase, sel2(b < K - LT, xmulc(prL, t2n)));   // :784
-				const float2 outM = make_output(phase, maxE, pinM);       // :788
+				const float2 outM = make_output_q(phase, maxE, pinM);     // :788
 #pragma unroll
 				for (int c = 0; c < CT; ++c) {
 					float2 oc = outM;
 					if (CT > 1) {
 						const float2 cph = xmul(outM, xmulc(inB[c], pinM)); // :796-797
-						const float2 other = make_output(cph, eB[c], inB[c]);
+						const float2 other = make_output_q(cph, eB[c], inB[c]);
 						if (c != m) oc = other;
 					}
 					// unconditional: out-of-range steps only produce values that every consumer masks
@@ -229,6 +239,13 @@ __global__ void __launch_bounds__(32) k_chain_direct(Ctx x) {
 					if (carryE && bIn) myE[c][b] = eB[c];
 					U.y[c][i][lane] = oc;
 				}
+			};
+			if (!farAny) { // fully unrolled, branch-free: one basic block the scheduler can interleave
+#pragma unroll
+				for (int i = 0; i < CHAIN_CH; ++i) step(i, std::false_type{});
+			} else {
+#pragma unroll 1
+				for (int i = 0; i < CHAIN_CH; ++i) step(i, std::true_type{});
 			}
 			__syncwarp();
 			// ---------------- write the chunk's finals back, 64 B per block ----------------

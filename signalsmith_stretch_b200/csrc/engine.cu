@@ -169,6 +169,8 @@ static int prof_mark(b200s_engine *e, int kind, bool begin) {
 	} while (0)
 
 typedef void (*ChainKernel)(Ctx);
+static ChainKernel analyse_kernel(const Cfg &g) { return g.K == 3072 ? k_analyse<3072> : g.K == 2560 ? k_analyse<2560> : k_analyse<0>; }
+static ChainKernel synth_kernel(const Cfg &g) { return g.K == 3072 ? k_synth<3072> : g.K == 2560 ? k_synth<2560> : k_synth<0>; }
 template <int CT>
 static ChainKernel chain_kernel_for(int L, bool direct) {
 	switch (L) {
@@ -345,9 +347,9 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	}
 	e->histCur = 0;
 #ifndef B200S_EMU
-	CK(cudaFuncSetAttribute(k_analyse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_analyse(g)));
+	CK(cudaFuncSetAttribute(analyse_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_analyse(g)));
 	CK(cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep(g)));
-	CK(cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_synth(g)));
+	CK(cudaFuncSetAttribute(synth_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_synth(g)));
 	CK(cudaFuncSetAttribute(k_flush_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * g.B)));
 	CK(cudaFuncSetAttribute(chain_kernel(g, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, false)));
 	CK(cudaFuncSetAttribute(chain_kernel(g, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, true)));
@@ -403,7 +405,8 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	const int F = frames_bound(g, nOut);
 	PROF(PK_PLAN, B200S_LAUNCH(k_plan, dim3(g.S), dim3(kThreads), 0, e->stream, x));
 	if (F > 0) {
-		PROF(PK_ANALYSE, B200S_LAUNCH(k_analyse, dim3(2 * F, g.C, g.S), dim3(kThreads), smem_analyse(g), e->stream, x));
+		ChainKernel ka = analyse_kernel(g);
+		PROF(PK_ANALYSE, B200S_LAUNCH(ka, dim3(2 * F, g.C, g.S), dim3(kThreads), smem_analyse(g), e->stream, x));
 		// Pure time-stretch (no frequency map, no formants): the chain forms its terms directly from
 		// the spectra and k_prep is skipped; otherwise k_prep produces the coefficient arrays.
 		const bool plain = !(e->prm.mapN > 0 || e->prm.freqMultiplier != 1.0f) && e->prm.formantMultiplier == 1.0f;
@@ -412,7 +415,8 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 		ChainKernel kc = chain_kernel(g, plain);
 		PROF(PK_CHAIN, B200S_LAUNCH(kc, grid, block, smem_chain(g, plain), e->stream, x));
 	}
-	PROF(PK_SYNTH, B200S_LAUNCH(k_synth, dim3(g.C, g.S), dim3(kThreads), smem_synth(g), e->stream, x));
+	ChainKernel ks = synth_kernel(g);
+	PROF(PK_SYNTH, B200S_LAUNCH(ks, dim3(g.C, g.S), dim3(kThreads), smem_synth(g), e->stream, x));
 	PROF(PK_COMMIT, B200S_LAUNCH(k_commit, dim3(g.S), dim3(kThreads), 0, e->stream, x));
 	e->histCur ^= 1;
 	return 0;
@@ -752,6 +756,25 @@ int b200s_profile_end(b200s_engine *e, float *ms, int *counts, int n) {
 	for (cudaEvent_t ev : e->profEv) cudaEventDestroy(ev);
 	e->profEv.clear();
 	e->profKind.clear();
+	return 0;
+}
+
+// Device self-test of the branch-free division / square root used by the phase chain.
+int b200s_selftest_divsqrt(b200s_engine *e, long long n, long long seed, long long *divMismatch, long long *sqrtMismatch) {
+	if (!e || n <= 0) return B200S_EINVAL;
+	unsigned long long *d = 0;
+	int rc;
+	if ((rc = dalloc(e, &d, 2))) return rc;
+	CK(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+	const int threads = 256, blocks = 1184, per = (int)((n + (long long)threads * blocks - 1) / ((long long)threads * blocks));
+	B200S_LAUNCH(k_selftest_divsqrt, dim3(blocks), dim3(threads), 0, e->stream, (unsigned long long)seed, per, d);
+	CKL();
+	unsigned long long h[2] = {0, 0};
+	CK(cudaStreamSynchronize(e->stream));
+	CK(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+	cudaFree(d);
+	if (divMismatch) *divMismatch = (long long)h[0];
+	if (sqrtMismatch) *sqrtMismatch = (long long)h[1];
 	return 0;
 }
 

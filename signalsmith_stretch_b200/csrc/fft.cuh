@@ -200,16 +200,27 @@ __device__ __forceinline__ float2 twiddle_at(const float2 *__restrict__ tw, int 
 }
 
 // One Stockham pass of radix R over `src` -> `dst` (padded shared-memory buffers, K points).
-// Ns = product of the radices of earlier passes (a power of two).
-template <int R, bool INV>
-__device__ __forceinline__ void fft_pass(int K, int Ns, const float2 *src, float2 *dst, const float2 *__restrict__ tw, int tid, int nthr) {
+// Ns = product of the radices of earlier passes (a power of two).  KC/NSC > 0: K and Ns are
+// compile-time constants (the preset sizes), which turns every per-element index into
+// base + immediate: fpad(j + q*nb) = fpad(j) + q*(nb + nb/16) when 16 | nb, and likewise for the
+// scattered stores (Ns == 1: fpad(R*j + q) with R == 16 is 17*j + q).
+template <int R, bool INV, int KC = 0, int NSC = 0, int NT = 0>
+__device__ __forceinline__ void fft_pass(int Krt, int NsRt, const float2 *src, float2 *dst, const float2 *__restrict__ tw, int tid, int nthrRt) {
+	const int K = KC ? KC : Krt, Ns = NSC ? NSC : NsRt, nthr = NT ? NT : nthrRt;
 	const int nb = K / R;
 	const int twStep = K / (Ns * R);
 	const int mask = Ns - 1;
+	constexpr bool kConstStride = KC > 0 && NSC > 0 && ((KC / R) % 16 == 0) && (NSC % 16 == 0 || (NSC == 1 && R == 16));
 	for (int j = tid; j < nb; j += nthr) {
 		const int k = j & mask;
 		float2 v[R];
-		static_for<R>([&](auto qc) { v[decltype(qc)::value] = src[fpad(j + decltype(qc)::value * nb)]; });
+		if constexpr (kConstStride) {
+			constexpr int S1 = (KC / R) + (KC / R) / 16;
+			const float2 *sp = src + fpad(j);
+			static_for<R>([&](auto qc) { v[decltype(qc)::value] = sp[decltype(qc)::value * S1]; });
+		} else {
+			static_for<R>([&](auto qc) { v[decltype(qc)::value] = src[fpad(j + decltype(qc)::value * nb)]; });
+		}
 		if (Ns > 1) {
 			// w^q = exp(-+2*pi*i*q*k/(Ns*R)): exact table entries for q = 1,2,4,8, products for the rest
 			const int t = k * twStep;
@@ -233,37 +244,61 @@ __device__ __forceinline__ void fft_pass(int K, int Ns, const float2 *src, float
 		}
 		SmallDFT<R, INV>::run(v);
 		const int j0 = (j - k) * R + k;
-		static_for<R>([&](auto qc) { dst[fpad(j0 + decltype(qc)::value * Ns)] = v[decltype(qc)::value]; });
+		if constexpr (kConstStride) {
+			if constexpr (NSC == 1) {
+				float2 *dp = dst + 17 * j;
+				static_for<R>([&](auto qc) { dp[decltype(qc)::value] = v[decltype(qc)::value]; });
+			} else {
+				constexpr int S2 = NSC + NSC / 16;
+				float2 *dp = dst + fpad(j0);
+				static_for<R>([&](auto qc) { dp[decltype(qc)::value * S2] = v[decltype(qc)::value]; });
+			}
+		} else {
+			static_for<R>([&](auto qc) { dst[fpad(j0 + decltype(qc)::value * Ns)] = v[decltype(qc)::value]; });
+		}
 	}
 }
 
 // Full K-point FFT of bufA (ping-pong with bufB, both fft_buf_len(K) float2, indexed through
 // fpad()).  Returns the buffer holding the result.  Every thread of the block must call this (it
 // contains __syncthreads()); the input must be complete and visible (caller syncs before).
-template <bool INV>
+// KT = 3072 / 2560 (presetDefault / presetCheaper at 44.1-48 kHz): fully specialised 3-pass plans
+// 16*16*12 / 16*16*10 with 256 threads; KT = 0: run-time plan from cfg.radix[].
+template <bool INV, int KT = 0>
 __device__ float2 *fft_run(const Cfg &cfg, float2 *bufA, float2 *bufB, const float2 *__restrict__ tw, int tid, int nthr) {
-	float2 *src = bufA, *dst = bufB;
-	int Ns = 1;
-	for (int st = 0; st < cfg.nStages; ++st) {
-		const int R = cfg.radix[st];
-		switch (R) {
-		case 16: fft_pass<16, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
-		case 12: fft_pass<12, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
-		case 10: fft_pass<10, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
-		case 8: fft_pass<8, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
-		case 6: fft_pass<6, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
-		case 5: fft_pass<5, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
-		case 4: fft_pass<4, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
-		case 3: fft_pass<3, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
-		default: fft_pass<2, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
-		}
+	if constexpr (KT == 3072 || KT == 2560) {
+		constexpr int RL = KT == 3072 ? 12 : 10;
+		fft_pass<16, INV, KT, 1, 256>(KT, 1, bufA, bufB, tw, tid, 256);
 		__syncthreads();
-		float2 *t = src;
-		src = dst;
-		dst = t;
-		Ns *= R;
+		fft_pass<16, INV, KT, 16, 256>(KT, 16, bufB, bufA, tw, tid, 256);
+		__syncthreads();
+		fft_pass<RL, INV, KT, 256, 256>(KT, 256, bufA, bufB, tw, tid, 256);
+		__syncthreads();
+		return bufB;
+	} else {
+		float2 *src = bufA, *dst = bufB;
+		int Ns = 1;
+		for (int st = 0; st < cfg.nStages; ++st) {
+			const int R = cfg.radix[st];
+			switch (R) {
+			case 16: fft_pass<16, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
+			case 12: fft_pass<12, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
+			case 10: fft_pass<10, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
+			case 8: fft_pass<8, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
+			case 6: fft_pass<6, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
+			case 5: fft_pass<5, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
+			case 4: fft_pass<4, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
+			case 3: fft_pass<3, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
+			default: fft_pass<2, INV>(cfg.K, Ns, src, dst, tw, tid, nthr); break;
+			}
+			__syncthreads();
+			float2 *t = src;
+			src = dst;
+			dst = t;
+			Ns *= R;
+		}
+		return src;
 	}
-	return src;
 }
 
 } // namespace b200s

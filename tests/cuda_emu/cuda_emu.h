@@ -118,6 +118,15 @@ template <typename T>
 static inline T __shfl_down_sync(unsigned, T v, int d) { return emu::shfl_from(v, (emu::t_tid & 31) + d); }
 template <typename T>
 static inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl_from(v, src); }
+static inline int __any_sync(unsigned, int pred) {
+	int r = 0;
+	for (int l = 0; l < 32; ++l) r |= emu::shfl_from(pred ? 1 : 0, l);
+	return r;
+}
+static inline float __fmaf_rn(float a, float b, float c) { return std::fma(a, b, c); }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline void atomicAdd(unsigned long long *p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 
 #define B200S_LAUNCH(kernel, grid, block, smem, stream, ...) \
 	emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
