@@ -39,6 +39,12 @@ RATIO_OUT = 0.8  # output length / input length
 # compulsory HBM traffic per block-channel for this configuration
 # (input read + history append + 2 analysis gathers + output/energy state + OLA ring + output)
 ALGO_BYTES_PER_BLOCK_CHANNEL = 186048
+# --config 3 / 4 (not the driver's default): BASELINE configs[2] / [3] on one GPU, rate 1
+# (no re-analysis: 209 280 B per block-channel)
+EXTRA = {3: dict(channels=1, semitones=7.0, tonality=8000.0 / 48000, formant=False, algo=209280,
+                 name="BASELINE configs[2]: batch=1024/GPU mono 48 kHz presetDefault, +7 semitones, 8 kHz tonality limit"),
+         4: dict(channels=2, semitones=12.0, tonality=0.0, formant=True, algo=209280,
+                 name="BASELINE configs[3]: stereo 48 kHz presetDefault, +12 semitones, formant compensation, base 200 Hz")}
 METRIC = "audio output samples/sec (batched streams, per channel)"
 
 
@@ -204,7 +210,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="streams per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4], help="BASELINE config (default 2 = the headline)")
     args = ap.parse_args()
+    if args.config != 2:
+        global CHANNELS, RATIO_OUT, ALGO_BYTES_PER_BLOCK_CHANNEL
+        CHANNELS, RATIO_OUT, ALGO_BYTES_PER_BLOCK_CHANNEL = EXTRA[args.config]["channels"], 1.0, EXTRA[args.config]["algo"]
+        args.no_cpu_baseline = True
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -231,6 +242,11 @@ def main():
     lo, _hi = shard_range(args.batch * world, rank, world)  # this rank's streams of the global batch
     eng = BatchStretch(args.batch, device=local_rank)
     eng.presetDefault(CHANNELS, float(SR))
+    if args.config != 2:
+        eng.setTransposeSemitones(EXTRA[args.config]["semitones"], EXTRA[args.config]["tonality"])
+        if EXTRA[args.config]["formant"]:
+            eng.setFormantFactor(1.0, True)
+            eng.setFormantBase(200.0 / SR)
     eng.reserve(w["n_in"], w["n_out"])
 
     # three distinct input buffers (each >> L2), consecutive seconds of each stream's audio
@@ -316,7 +332,8 @@ def main():
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tmax / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config_dict(w, world), "clocks": clk,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(config_dict(w, world), **({} if args.config == 2 else {"workload": EXTRA[args.config]["name"]})), "clocks": clk,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()

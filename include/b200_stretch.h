@@ -47,6 +47,9 @@ int b200s_version(int *major, int *minor, int *patch); /* reference `version[3]`
 /* Use an existing CUDA stream (a cudaStream_t passed as void*) instead of the handle's own. */
 int b200s_set_stream(b200s_engine *e, void *cuda_stream);
 int b200s_synchronize(b200s_engine *e);
+/* process() can split the batch into up to 4 sub-batches on prioritised CUDA streams so that the
+ * different kernels of its launch sequence overlap (default 1 = off). */
+int b200s_set_sub_batches(b200s_engine *e, int n);
 
 /* ---- configuration: presetDefault / presetCheaper / configure / reset  (:49-94) ---- */
 int b200s_preset_default(b200s_engine *e, int channels, float sample_rate, int split_computation);

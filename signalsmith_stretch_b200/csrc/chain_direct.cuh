@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(32) k_chain_direct(Ctx x) {
 	const int K = g.K;
 	B200S_DYN_SHARED
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int s = blockIdx.x * (blockDim.x >> 5) + warp;
-	if (s >= g.S) return;
+	const int s = x.sBase + blockIdx.x * (blockDim.x >> 5) + warp;
+	if (s >= x.sBase + x.sCount) return;
 	const Call cl = x.call[s];
 	if (cl.nFrames == 0) return;
 	constexpr int D = LT + 1;

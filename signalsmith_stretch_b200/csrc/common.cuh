@@ -109,6 +109,9 @@ struct Ctx {
 	Call *call;    // [S]
 	float2 *spec, *Y, *cPI, *cFT, *cT1, *cT2;
 	float *cE;
+	// sub-batch of streams this launch covers (the batch is processed as a few sub-batches on
+	// prioritised CUDA streams so that different kernels of the sequence overlap on the SMs)
+	int sBase, sCount;
 	// I/O of the current call
 	const float *in;
 	float *out;

@@ -29,6 +29,11 @@ struct b200s_engine {
 	Params prm;
 	cudaStream_t stream = 0;
 	bool ownStream = false;
+	// sub-batch pipeline: process() splits the batch over these prioritised streams (see process_impl)
+	static const int kMaxSub = 4;
+	int nSub = 1, maxSub = 1;
+	cudaStream_t subStream[kMaxSub] = {0, 0, 0, 0};
+	cudaEvent_t evBegin = 0, evSubDone[kMaxSub] = {0, 0, 0, 0};
 	cudaEvent_t evStart = 0, evStop = 0;
 	long long launches = 0;
 	std::string err;
@@ -120,6 +125,7 @@ static Ctx make_ctx(b200s_engine *e) {
 	x.pend = e->dPend; x.pendWp = e->dPendWp;
 	x.stIn = e->dStIn; x.stPrev = e->dStPrev; x.stOut = e->dStOut; x.stPredE = e->dStPredE;
 	x.maxFrames = e->maxFrames;
+	x.sBase = 0; x.sCount = e->S;
 	x.frames = e->dFrames; x.call = e->dCall;
 	x.spec = e->dSpec; x.Y = e->dY; x.cPI = e->dPI; x.cFT = e->dFT; x.cT1 = e->dT1; x.cT2 = e->dT2; x.cE = e->dE;
 	return x;
@@ -403,21 +409,40 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	x.inChanStride = inChanStride; x.inStreamStride = inStreamStride;
 	x.outChanStride = outChanStride; x.outStreamStride = outStreamStride;
 	const int F = frames_bound(g, nOut);
-	PROF(PK_PLAN, B200S_LAUNCH(k_plan, dim3(g.S), dim3(kThreads), 0, e->stream, x));
-	if (F > 0) {
-		ChainKernel ka = analyse_kernel(g);
-		PROF(PK_ANALYSE, B200S_LAUNCH(ka, dim3(2 * F, g.C, g.S), dim3(kThreads), smem_analyse(g), e->stream, x));
-		// Pure time-stretch (no frequency map, no formants): the chain forms its terms directly from
-		// the spectra and k_prep is skipped; otherwise k_prep produces the coefficient arrays.
-		const bool plain = !(e->prm.mapN > 0 || e->prm.freqMultiplier != 1.0f) && e->prm.formantMultiplier == 1.0f;
-		if (!plain) PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, g.S), dim3(kThreads), smem_prep(g), e->stream, x));
-		dim3 grid((g.S + kChainWarps - 1) / kChainWarps), block(32 * kChainWarps);
-		ChainKernel kc = chain_kernel(g, plain);
-		PROF(PK_CHAIN, B200S_LAUNCH(kc, grid, block, smem_chain(g, plain), e->stream, x));
+	// Sub-batch pipeline: the streams of the batch are independent, so the launch sequence is issued
+	// per sub-batch on its own CUDA stream (descending priority).  Sub-batch 0's chain then runs while
+	// sub-batch 1 is still in its FFT kernel, and so on: the latency-bound wavefront kernel and the
+	// throughput-bound FFT kernels share the SMs instead of taking turns.  Per-kernel profiling
+	// (b200s_profile_begin) runs unsplit on the main stream so that the event pairs time one kernel each.
+	const int nSub = (e->profiling || e->nSub <= 1 || g.S < 64) ? 1 : e->nSub;
+	if (nSub > 1) CK(cudaEventRecord(e->evBegin, e->stream));
+	const bool plain = !(e->prm.mapN > 0 || e->prm.freqMultiplier != 1.0f) && e->prm.formantMultiplier == 1.0f;
+	for (int sub = 0; sub < nSub; ++sub) {
+		cudaStream_t st = nSub > 1 ? e->subStream[sub] : e->stream;
+		if (nSub > 1) CK(cudaStreamWaitEvent(st, e->evBegin, 0));
+		x.sBase = (int)((long long)g.S * sub / nSub);
+		x.sCount = (int)((long long)g.S * (sub + 1) / nSub) - x.sBase;
+		{ // (profiling implies nSub == 1, i.e. st == e->stream, which is where PROF() records its events)
+			PROF(PK_PLAN, B200S_LAUNCH(k_plan, dim3(x.sCount), dim3(kThreads), 0, st, x));
+			if (F > 0) {
+				ChainKernel ka = analyse_kernel(g);
+				PROF(PK_ANALYSE, B200S_LAUNCH(ka, dim3(2 * F, g.C, x.sCount), dim3(kThreads), smem_analyse(g), st, x));
+				// Pure time-stretch (no frequency map, no formants): the chain forms its terms directly from
+				// the spectra and k_prep is skipped; otherwise k_prep produces the coefficient arrays.
+				if (!plain) PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g), st, x));
+				dim3 grid((x.sCount + kChainWarps - 1) / kChainWarps), block(32 * kChainWarps);
+				ChainKernel kc = chain_kernel(g, plain);
+				PROF(PK_CHAIN, B200S_LAUNCH(kc, grid, block, smem_chain(g, plain), st, x));
+			}
+			ChainKernel ks = synth_kernel(g);
+			PROF(PK_SYNTH, B200S_LAUNCH(ks, dim3(g.C, x.sCount), dim3(kThreads), smem_synth(g), st, x));
+			PROF(PK_COMMIT, B200S_LAUNCH(k_commit, dim3(x.sCount), dim3(kThreads), 0, st, x));
+		}
+		if (nSub > 1) {
+			CK(cudaEventRecord(e->evSubDone[sub], st));
+			CK(cudaStreamWaitEvent(e->stream, e->evSubDone[sub], 0));
+		}
 	}
-	ChainKernel ks = synth_kernel(g);
-	PROF(PK_SYNTH, B200S_LAUNCH(ks, dim3(g.C, g.S), dim3(kThreads), smem_synth(g), e->stream, x));
-	PROF(PK_COMMIT, B200S_LAUNCH(k_commit, dim3(g.S), dim3(kThreads), 0, e->stream, x));
 	e->histCur ^= 1;
 	return 0;
 }
@@ -521,6 +546,23 @@ int b200s_create(int batch, long seed, int device, b200s_engine **out) {
 		return B200S_ECUDA;
 	}
 	e->ownStream = true;
+	{ // sub-batch streams: highest priority first
+		int lo = 0, hi = 0;
+		cudaDeviceGetStreamPriorityRange(&lo, &hi);
+		bool ok = cudaEventCreateWithFlags(&e->evBegin, cudaEventDisableTiming) == cudaSuccess;
+		for (int i = 0; i < b200s_engine::kMaxSub && ok; ++i) {
+			int pr = hi + i;
+			if (pr > lo) pr = lo;
+			ok = cudaStreamCreateWithPriority(&e->subStream[i], cudaStreamNonBlocking, pr) == cudaSuccess &&
+			     cudaEventCreateWithFlags(&e->evSubDone[i], cudaEventDisableTiming) == cudaSuccess;
+		}
+		// Measured on B200 (profiles/r01_bench_v7_subbatch.json): splitting the 1024-stream batch over 4
+		// prioritised streams is SLOWER (11.9 vs 9.7 ms/step) -- the wavefront kernel is bound by per-warp
+		// latency, not by occupancy, so co-running FFT CTAs only steal its issue slots.  Kept (off) for
+		// batches large enough to oversubscribe the SMs; b200s_set_sub_batches() turns it on.
+		e->nSub = 1;
+		e->maxSub = ok ? b200s_engine::kMaxSub : 1;
+	}
 	*out = e;
 	return 0;
 }
@@ -531,6 +573,11 @@ void b200s_destroy(b200s_engine *e) {
 	free_all(e);
 	dfree(e->dMapIn);
 	dfree(e->dMapOut);
+	for (int i = 0; i < b200s_engine::kMaxSub; ++i) {
+		if (e->subStream[i]) cudaStreamDestroy(e->subStream[i]);
+		if (e->evSubDone[i]) cudaEventDestroy(e->evSubDone[i]);
+	}
+	if (e->evBegin) cudaEventDestroy(e->evBegin);
 	if (e->evStart) cudaEventDestroy(e->evStart);
 	if (e->evStop) cudaEventDestroy(e->evStop);
 	if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
@@ -549,6 +596,11 @@ int b200s_set_stream(b200s_engine *e, void *cuda_stream) {
 	if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
 	e->stream = (cudaStream_t)cuda_stream;
 	e->ownStream = false;
+	return 0;
+}
+int b200s_set_sub_batches(b200s_engine *e, int n) {
+	if (!e || n < 1) return B200S_EINVAL;
+	e->nSub = n > e->maxSub ? e->maxSub : n;
 	return 0;
 }
 int b200s_synchronize(b200s_engine *e) {
