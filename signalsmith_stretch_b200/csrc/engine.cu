@@ -151,7 +151,7 @@ static double bessel0(double x) {
 }
 
 static const int kThreads = 256;
-static size_t smem_analyse(const Cfg &g) { return sizeof(float2) * 2 * fft_buf_len(g.K); }
+static size_t smem_analyse(const Cfg &g) { return sizeof(float2) * 2 * fft_buf_len(g.K) + sizeof(float) * (g.B + 4); }
 static size_t smem_prep(const Cfg &g) { return sizeof(float) * (7 * (size_t)g.K + 8); }
 static size_t smem_synth(const Cfg &g) { return sizeof(float2) * 2 * fft_buf_len(g.K) + sizeof(float) * 2 * g.pendLen; }
 
@@ -426,7 +426,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 			PROF(PK_PLAN, B200S_LAUNCH(k_plan, dim3(x.sCount), dim3(kThreads), 0, st, x));
 			if (F > 0) {
 				ChainKernel ka = analyse_kernel(g);
-				PROF(PK_ANALYSE, B200S_LAUNCH(ka, dim3(2 * F, g.C, x.sCount), dim3(kThreads), smem_analyse(g), st, x));
+				PROF(PK_ANALYSE, B200S_LAUNCH(ka, dim3(std::min(2 * F * g.C, ANALYSE_CTAS_PER_STREAM), 1, x.sCount), dim3(kThreads), smem_analyse(g), st, x));
 				// Pure time-stretch (no frequency map, no formants): the chain forms its terms directly from
 				// the spectra and k_prep is skipped; otherwise k_prep produces the coefficient arrays.
 				if (!plain) PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g), st, x));
