@@ -87,6 +87,13 @@ struct Call {
 	int bypass;   // silence bypass (:240-271)
 	int nFrames;
 	int finalIn, finalPrev; // slots that become stIn / stPrev after the call
+	int nJobs;              // analyses of this call (entries of the stream's Job list)
+};
+
+// one windowed analysis FFT of the call (:333-376): block samples start at stream index `start`
+// (history ++ input), the spectrum goes to row `row` = (2*f + w)*C + c of the stream's `spec` scratch
+struct Job {
+	int start, row, c;
 };
 
 // everything a kernel needs, passed by value
@@ -107,6 +114,8 @@ struct Ctx {
 	int maxFrames;
 	Frame *frames; // [S][maxFrames]
 	Call *call;    // [S]
+	Job *jobs;     // [S][2*C*maxFrames], consecutive entries are transformed as one PAIR (fft2.cuh)
+	int inAligned; // input / history rows allow 16-byte cp.async (pointer, strides and lengths multiples of 4 floats)
 	float2 *spec, *Y, *cPI, *cFT, *cT1, *cT2;
 	float *cE;
 	// sub-batch of streams this launch covers (the batch is processed as a few sub-batches on

@@ -9,6 +9,8 @@
 #include <cmath>
 #include <complex>
 #include <cstdio>
+#include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -16,6 +18,8 @@
 #include "../../include/b200_stretch.h"
 #include "kernels.cuh"
 #include "chain_direct.cuh"
+#include "chain_direct2.cuh"
+#include "stft2.cuh"
 
 using namespace b200s;
 
@@ -58,6 +62,8 @@ struct b200s_engine {
 	int maxFrames = 0;
 	Frame *dFrames = 0;
 	Call *dCall = 0;
+	Job *dJobs = 0;
+	int numSMs = 148;
 	float2 *dSpec = 0, *dY = 0, *dPI = 0, *dFT = 0, *dT1 = 0, *dT2 = 0;
 	float *dE = 0;
 	// staging for the host-buffer API and for flush/outputSeek
@@ -104,7 +110,7 @@ static void free_all(b200s_engine *e) {
 	dfree(e->dWindow); dfree(e->dWinProd); dfree(e->dWpReset); dfree(e->dRot); dfree(e->dTwiddle); dfree(e->dPretw);
 	dfree(e->dSched); dfree(e->dHist[0]); dfree(e->dHist[1]); dfree(e->dPend); dfree(e->dPendWp);
 	dfree(e->dStIn); dfree(e->dStPrev); dfree(e->dStOut); dfree(e->dStPredE);
-	dfree(e->dFrames); dfree(e->dCall); dfree(e->dSpec); dfree(e->dY); dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dE);
+	dfree(e->dFrames); dfree(e->dCall); dfree(e->dJobs); dfree(e->dSpec); dfree(e->dY); dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dE);
 	dfree(e->dIn); dfree(e->dOut); dfree(e->dZero); dfree(e->dTmp);
 	e->maxFrames = 0;
 	e->inCap = e->outCap = e->zeroCap = e->tmpCap = 0;
@@ -126,7 +132,7 @@ static Ctx make_ctx(b200s_engine *e) {
 	x.stIn = e->dStIn; x.stPrev = e->dStPrev; x.stOut = e->dStOut; x.stPredE = e->dStPredE;
 	x.maxFrames = e->maxFrames;
 	x.sBase = 0; x.sCount = e->S;
-	x.frames = e->dFrames; x.call = e->dCall;
+	x.frames = e->dFrames; x.call = e->dCall; x.jobs = e->dJobs;
 	x.spec = e->dSpec; x.Y = e->dY; x.cPI = e->dPI; x.cFT = e->dFT; x.cT1 = e->dT1; x.cT2 = e->dT2; x.cE = e->dE;
 	return x;
 }
@@ -176,6 +182,14 @@ static int prof_mark(b200s_engine *e, int kind, bool begin) {
 
 typedef void (*ChainKernel)(Ctx);
 static ChainKernel analyse_kernel(const Cfg &g) { return g.K == 3072 ? k_analyse<3072> : g.K == 2560 ? k_analyse<2560> : k_analyse<0>; }
+// paired in-place FFT kernels (stft2.cuh) for the preset sizes
+static bool use_pair_fft(const Cfg &g) {
+	static int v1 = -1;
+	if (v1 < 0) v1 = getenv("B200S_FFT_V1") ? 1 : 0; // A/B switch for profiling the first-generation kernels
+	return !v1 && (g.K == 3072 || g.K == 2560);
+}
+static ChainKernel analyse2_kernel(const Cfg &g) { return g.K == 3072 ? k_analyse2<3072> : k_analyse2<2560>; }
+static ChainKernel synth2_kernel(const Cfg &g) { return g.K == 3072 ? k_synth2<3072> : k_synth2<2560>; }
 static ChainKernel synth_kernel(const Cfg &g) { return g.K == 3072 ? k_synth<3072> : g.K == 2560 ? k_synth<2560> : k_synth<0>; }
 template <int CT>
 static ChainKernel chain_kernel_for(int L, bool direct) {
@@ -189,6 +203,31 @@ static ChainKernel chain_kernel_for(int L, bool direct) {
 	case 7: return direct ? k_chain_direct<CT, 7> : k_chain<CT, 7, false>;
 	default: return direct ? k_chain_direct<CT, 8> : k_chain<CT, 8, false>;
 	}
+}
+// second-generation direct chain: lane = (block, channel), several warps per stream (chain_direct2.cuh)
+template <int CT>
+static ChainKernel chain2_kernel_for(int L) {
+	switch (L) {
+	case 1: return k_chain_direct2<CT, 1>;
+	case 2: return k_chain_direct2<CT, 2>;
+	case 3: return k_chain_direct2<CT, 3>;
+	case 4: return k_chain_direct2<CT, 4>;
+	case 5: return k_chain_direct2<CT, 5>;
+	case 6: return k_chain_direct2<CT, 6>;
+	case 7: return k_chain_direct2<CT, 7>;
+	default: return k_chain_direct2<CT, 8>;
+	}
+}
+static ChainKernel chain2_kernel(const Cfg &g) { return g.C == 1 ? chain2_kernel_for<1>(g.L) : chain2_kernel_for<2>(g.L); }
+// warps per stream for a call of nOut output samples: one per 32/C blocks (blocks trigger every H samples)
+static int chain2_warps(const Cfg &g, int nOut) {
+	const int blocks = (nOut + g.H - 1) / g.H, bpw = 32 / g.C;
+	return std::max(1, std::min(CH2_MAXW, (blocks + bpw - 1) / bpw));
+}
+static bool use_chain_v1() {
+	static int v = -1;
+	if (v < 0) v = getenv("B200S_CHAIN_V1") ? 1 : 0; // A/B switch for profiling the first-generation kernel
+	return v == 1;
 }
 static ChainKernel chain_kernel(const Cfg &g, bool direct) {
 	return g.C == 1 ? chain_kernel_for<1>(g.L, direct) : chain_kernel_for<2>(g.L, direct);
@@ -359,6 +398,15 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	CK(cudaFuncSetAttribute(k_flush_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * g.B)));
 	CK(cudaFuncSetAttribute(chain_kernel(g, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, false)));
 	CK(cudaFuncSetAttribute(chain_kernel(g, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, true)));
+	CK(cudaFuncSetAttribute(chain2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain2(g.C, CH2_MAXW)));
+	if (use_pair_fft(g)) {
+		CK(cudaFuncSetAttribute(analyse2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_analyse2(g)));
+		CK(cudaFuncSetAttribute(synth2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_synth2(g)));
+	}
+	{
+		int n = 0;
+		if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, e->device) == cudaSuccess && n > 0) e->numSMs = n;
+	}
 #endif
 	e->configured = true;
 	return reset_impl(e, true);
@@ -374,6 +422,7 @@ static int ensure_scratch(b200s_engine *e, int nOut) {
 	const size_t n = (size_t)g.S * need * g.C * g.K;
 	int rc;
 	if ((rc = dalloc(e, &e->dFrames, (size_t)g.S * need))) return rc;
+	if ((rc = dalloc(e, &e->dJobs, (size_t)g.S * need * 2 * g.C))) return rc;
 	if ((rc = dalloc(e, &e->dSpec, 2 * n))) return rc;
 	if ((rc = dalloc(e, &e->dY, n))) return rc;
 	if ((rc = dalloc(e, &e->dPI, n))) return rc;
@@ -408,6 +457,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	x.in = dIn; x.out = dOut; x.nIn = nIn; x.nOut = nOut;
 	x.inChanStride = inChanStride; x.inStreamStride = inStreamStride;
 	x.outChanStride = outChanStride; x.outStreamStride = outStreamStride;
+	x.inAligned = ((uintptr_t)dIn % 16 == 0) && inChanStride % 4 == 0 && inStreamStride % 4 == 0 && nIn % 4 == 0 && g.histLen % 4 == 0;
 	const int F = frames_bound(g, nOut);
 	// Sub-batch pipeline: the streams of the batch are independent, so the launch sequence is issued
 	// per sub-batch on its own CUDA stream (descending priority).  Sub-batch 0's chain then runs while
@@ -425,17 +475,33 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 		{ // (profiling implies nSub == 1, i.e. st == e->stream, which is where PROF() records its events)
 			PROF(PK_PLAN, B200S_LAUNCH(k_plan, dim3(x.sCount), dim3(kThreads), 0, st, x));
 			if (F > 0) {
-				ChainKernel ka = analyse_kernel(g);
-				PROF(PK_ANALYSE, B200S_LAUNCH(ka, dim3(std::min(2 * F * g.C, ANALYSE_CTAS_PER_STREAM), 1, x.sCount), dim3(kThreads), smem_analyse(g), st, x));
+				if (use_pair_fft(g)) { // persistent CTAs, two per SM, over the (stream, job pair) items
+					const long long items = (long long)x.sCount * g.C * x.maxFrames;
+					const int grid = (int)std::min<long long>(items, 2LL * e->numSMs);
+					PROF(PK_ANALYSE, B200S_LAUNCH(analyse2_kernel(g), dim3(grid), dim3(256), smem_analyse2(g), st, x));
+				} else {
+					ChainKernel ka = analyse_kernel(g);
+					PROF(PK_ANALYSE, B200S_LAUNCH(ka, dim3(std::min(2 * F * g.C, ANALYSE_CTAS_PER_STREAM), 1, x.sCount), dim3(kThreads), smem_analyse(g), st, x));
+				}
 				// Pure time-stretch (no frequency map, no formants): the chain forms its terms directly from
 				// the spectra and k_prep is skipped; otherwise k_prep produces the coefficient arrays.
 				if (!plain) PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g), st, x));
-				dim3 grid((x.sCount + kChainWarps - 1) / kChainWarps), block(32 * kChainWarps);
-				ChainKernel kc = chain_kernel(g, plain);
-				PROF(PK_CHAIN, B200S_LAUNCH(kc, grid, block, smem_chain(g, plain), st, x));
+				if (plain && !use_chain_v1()) {
+					const int W = chain2_warps(g, nOut);
+					ChainKernel kc = chain2_kernel(g);
+					PROF(PK_CHAIN, B200S_LAUNCH(kc, dim3(x.sCount), dim3(32 * W), smem_chain2(g.C, W), st, x));
+				} else {
+					dim3 grid((x.sCount + kChainWarps - 1) / kChainWarps), block(32 * kChainWarps);
+					ChainKernel kc = chain_kernel(g, plain);
+					PROF(PK_CHAIN, B200S_LAUNCH(kc, grid, block, smem_chain(g, plain), st, x));
+				}
 			}
-			ChainKernel ks = synth_kernel(g);
-			PROF(PK_SYNTH, B200S_LAUNCH(ks, dim3(g.C, x.sCount), dim3(kThreads), smem_synth(g), st, x));
+			if (use_pair_fft(g)) {
+				PROF(PK_SYNTH, B200S_LAUNCH(synth2_kernel(g), dim3(g.C, x.sCount), dim3(256), smem_synth2(g), st, x));
+			} else {
+				ChainKernel ks = synth_kernel(g);
+				PROF(PK_SYNTH, B200S_LAUNCH(ks, dim3(g.C, x.sCount), dim3(kThreads), smem_synth(g), st, x));
+			}
 			PROF(PK_COMMIT, B200S_LAUNCH(k_commit, dim3(x.sCount), dim3(kThreads), 0, st, x));
 		}
 		if (nSub > 1) {

@@ -1,0 +1,310 @@
+// stft2.cuh -- analysis and synthesis kernels for the preset FFT sizes on the PAIRED in-place FFT
+// (fft2.cuh).  Same results as k_analyse / k_synth (kernels.cuh), which stay for generic sizes.
+//
+//   k_analyse2  windowed modified real FFT of TWO analyses at a time (dependency analyseStep,
+//               reference call sites signalsmith-stretch.h:337,359).  Persistent CTAs walk the
+//               (stream, job pair) items of the call; the raw samples of the NEXT pair are copied to
+//               shared memory with 16-byte cp.async while the current FFT runs.
+//   k_synth2    inverse FFT of TWO consecutive blocks of one stream-channel at a time, synthesis
+//               window and overlap-add (synthesiseStep / readOutput / moveOutput, :397-414).  One
+//               sweep over the pending ring applies, per ring slot and in the reference's order,
+//               block A's contribution, the emission of the samples between the two blocks, and
+//               block B's contribution -- one read-modify-write per slot instead of three.
+#pragma once
+#include "fft2.cuh"
+#include "kernels.cuh"
+
+namespace b200s {
+
+#ifdef B200S_EMU
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) { memcpy(dst, src, 16); }
+#else
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+	unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+#endif
+
+__host__ __device__ __forceinline__ int stage_len(int B) { return (B + 8 + 3) & ~3; }
+
+// ---------------------------------------------------------------------------------------------
+// k_analyse2: grid = persistent CTAs (a multiple of the SM count), 256 threads.
+// dyn smem: PairGeo::LEN float4 (FFT pair) + 2 * stage_len(B) floats (raw samples of the next pair).
+// ---------------------------------------------------------------------------------------------
+template <int KT>
+__global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
+	using G = PairGeo<KT>;
+	const Cfg &g = x.cfg;
+	B200S_DYN_SHARED
+	float4 *buf = (float4 *)dyn_smem;
+	const int B = g.B, o = g.o, tid = threadIdx.x;
+	float *stA = (float *)(buf + G::LEN), *stB = stA + stage_len(B);
+	const PairTw tw = pair_tw_load<KT>(x.twiddle, tid);
+	const float2 pre0 = __ldg(x.pretw + tid); // exp(-i*pi*tid/N); element tid + 256*it gets a compile-time factor on top
+	const int PJ = g.C * x.maxFrames;         // pair slots per stream (2*C*maxFrames jobs)
+	const long long total = (long long)x.sCount * PJ;
+
+	struct Item {
+		int s, hasB;
+		Job a, b;
+	};
+	// item -> jobs; false when the stream has fewer pairs than slots
+	auto fetch = [&](long long it, Item &m) -> bool {
+		m.s = x.sBase + (int)(it / PJ);
+		const int p = (int)(it % PJ), nJ = x.call[m.s].nJobs;
+		if (2 * p >= nJ) return false;
+		const Job *jb = x.jobs + (size_t)m.s * 2 * g.C * x.maxFrames + 2 * p;
+		m.a = jb[0];
+		m.hasB = 2 * p + 1 < nJ;
+		m.b = m.hasB ? jb[1] : jb[0];
+		return true;
+	};
+	auto next_valid = [&](long long it, Item &m) -> long long {
+		while (it < total && !fetch(it, m)) it += gridDim.x;
+		return it;
+	};
+	// asynchronously copy the B samples (history ++ input) of one job into a staging buffer;
+	// aligned mode copies 16-byte chunks of the enclosing 4-aligned range (sample i lands at st[i + (start & 3)])
+	auto stage_job = [&](float *st, int s, const Job &j) {
+		const float *ib = x.in + (size_t)s * x.inStreamStride + (size_t)j.c * x.inChanStride;
+		const float *he = x.histCur + ((size_t)s * g.C + j.c) * g.histLen + g.histLen;
+		if (x.inAligned) {
+			const int sh = j.start & 3, a00 = j.start - sh, nCh = (B + sh + 3) >> 2;
+			for (int q = tid; q < nCh; q += 256) {
+				const int a0 = a00 + 4 * q;
+				if (a0 >= 0 ? (a0 < x.nIn) : (a0 >= -g.histLen)) cp_async16(st + 4 * q, a0 >= 0 ? ib + a0 : he + a0);
+				else *(float4 *)(st + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+			}
+		} else {
+			for (int i = tid; i < B; i += 256) {
+				const int a = j.start + i;
+				if (a < x.nIn && a >= -g.histLen) cp_async4(st + i, a >= 0 ? ib + a : he + a);
+				else st[i] = 0.f;
+			}
+		}
+	};
+	Item cur, nxt;
+	long long item = next_valid(blockIdx.x, cur);
+	if (item < total) {
+		stage_job(stA, cur.s, cur.a);
+		stage_job(stB, cur.s, cur.b);
+	}
+	while (item < total) {
+		float2 *dstA = x.spec + ((size_t)cur.s * 2 * x.maxFrames * g.C + cur.a.row) * g.K;
+		float2 *dstB = x.spec + ((size_t)cur.s * 2 * x.maxFrames * g.C + cur.b.row) * g.K;
+		cp_async_wait_all();
+		__syncthreads(); // staging complete and visible; previous unpack finished with buf
+#ifdef B200S_EMU_EXACT_FFT // test builds only: swap in the oracle's double FFT to isolate the non-FFT logic
+		{
+			const int shA = x.inAligned ? (cur.a.start & 3) : 0, shB = x.inAligned ? (cur.b.start & 3) : 0;
+			if (tid == 0) {
+				float *xw = (float *)buf;
+				for (int i = 0; i < B; ++i) xw[i] = fmul(stA[i + shA], x.window[i]);
+				emu_exact_forward(xw, B, o, 2 * KT, dstA);
+				if (cur.hasB) {
+					for (int i = 0; i < B; ++i) xw[i] = fmul(stB[i + shB], x.window[i]);
+					emu_exact_forward(xw, B, o, 2 * KT, dstB);
+				}
+			}
+			__syncthreads();
+			item = next_valid(item + gridDim.x, nxt);
+			if (item < total) {
+				stage_job(stA, nxt.s, nxt.a);
+				stage_job(stB, nxt.s, nxt.b);
+			}
+			cur = nxt;
+			continue;
+		}
+#endif
+		{ // ---- load stage: window, wrap-sign fold, half-bin pre-twiddle
+			const int shA = x.inAligned ? (cur.a.start & 3) : 0, shB = x.inAligned ? (cur.b.start & 3) : 0;
+			static_for<G::R3>([&](auto itc) {
+				constexpr int it = decltype(itc)::value;
+				const int n = tid + 256 * it, i0 = n + o, i1 = n + o - KT;
+				const bool in0 = i0 < B, in1 = i1 >= 0;
+				const float w0 = in0 ? __ldg(x.window + i0) : 0.f, w1 = in1 ? __ldg(x.window + i1) : 0.f;
+				const float a0 = in0 ? stA[i0 + shA] : 0.f, a1 = in1 ? stA[i1 + shA] : 0.f;
+				const float b0 = in0 ? stB[i0 + shB] : 0.f, b1 = in1 ? stB[i1 + shB] : 0.f;
+				// exp(-i*pi*n/N) = pre0 * exp(-i*pi*256*it/N), the second factor is a compile-time constant
+				constexpr float fc = float(ct::cosq(256 * it, 4 * KT)), fs = -float(ct::sinq(256 * it, 4 * KT));
+				const float2 pw = cmulf(pre0, make_float2(fc, fs));
+				const c2 t = c2{muls(f2_make(a0, b0), w0), muls(f2_make(a1, b1), w1)}; // (x0*w0) + i*(x1*w1)
+				st_c2(buf + G::slot_in(n), cmulw(t, pw.x, pw.y));
+			});
+		}
+		__syncthreads(); // staging consumed, buf complete
+		const long long nitem = next_valid(item + gridDim.x, nxt);
+		if (nitem < total) { // start the next pair's input on its way while this FFT runs
+			stage_job(stA, nxt.s, nxt.a);
+			stage_job(stB, nxt.s, nxt.b);
+		}
+		pair_fft<false, KT>(buf, tw, tid);
+		{ // ---- unpack: bin b = Z[b/2] (b even) or conj(Z[K-1-b/2]) (b odd), Z digit-reversed in buf
+			const bool hasB = cur.hasB;
+			static_for<G::R3>([&](auto itc) {
+				const int b = tid + 256 * decltype(itc)::value;
+				const int hb = b >> 1, k = (b & 1) ? KT - 1 - hb : hb;
+				const float4 z = buf[G::slot_out(k)];
+				const float sg = (b & 1) ? -1.f : 1.f;
+				dstA[b] = make_float2(z.x, sg * z.z);
+				if (hasB) dstB[b] = make_float2(z.y, sg * z.w);
+			});
+		}
+		item = nitem;
+		cur = nxt;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_synth2: grid (C, S), 256 threads, one CTA per stream-channel; blocks of the call two at a time.
+// dyn smem: PairGeo::LEN float4 (FFT pair) + pendLen floats (pending ring) + pendLen floats
+// (windowProducts ring; kept per channel so that no two CTAs share writable state).
+// ---------------------------------------------------------------------------------------------
+template <int KT>
+__global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
+	using G = PairGeo<KT>;
+	const Cfg &g = x.cfg;
+	B200S_DYN_SHARED
+	float4 *buf = (float4 *)dyn_smem;
+	float *pend = (float *)(buf + G::LEN), *wp = pend + g.pendLen;
+	const int c = blockIdx.x, s = x.sBase + blockIdx.y, tid = threadIdx.x;
+	const Call cl = x.call[s];
+	float *out = x.out + (size_t)s * x.outStreamStride + (size_t)c * x.outChanStride;
+	if (cl.bypass) { // :252-267
+		const float *in = x.in + (size_t)s * x.inStreamStride + (size_t)c * x.inChanStride;
+		for (int i = tid; i < x.nOut; i += 256) out[i] = x.nIn > 0 ? in[i % x.nIn] : 0.f;
+		return;
+	}
+	const int P = g.pendLen, B = g.B, o = g.o, addOff = g.addOff;
+	const float fN = (float)g.N;
+	float *gp = x.pend + ((size_t)s * g.C + c) * P, *gw = x.pendWp + ((size_t)s * g.C + c) * P;
+	for (int i = tid; i < P; i += 256) {
+		pend[i] = gp[i];
+		wp[i] = gw[i];
+	}
+	const PairTw tw = pair_tw_load<KT>(x.twiddle, tid);
+	const Frame *frames = x.frames + (size_t)s * x.maxFrames;
+	__syncthreads();
+	int head = 0, emitted = 0;
+	// emit n samples from the ring head, zero them behind (:408-414)
+	auto emit = [&](int n) {
+		for (int i = tid; i < n; i += 256) {
+			float v = 0.f;
+			if (i < P) {
+				int p = head + i;
+				if (p >= P) p -= P;
+				v = fdiv(pend[p], wp[p]);
+				pend[p] = 0.f;
+				wp[p] = B200S_ALMOST_ZERO;
+			}
+			out[emitted + i] = v;
+		}
+		head = (head + (n < P ? n : P)) % P; // n >= P leaves an all-clear ring; any head is fine
+		emitted += n;
+	};
+	for (int f = 0; f < cl.nFrames; f += 2) {
+		const bool hasB = f + 1 < cl.nFrames;
+		const int tA = frames[f].t;
+		// samples emitted between the two blocks; without a second block nothing is emitted inside the sweep
+		const int gap = hasB ? frames[f + 1].t - tA : 0;
+		const float2 *YA = x.Y + coef_off(x, s, f, c), *YB = x.Y + coef_off(x, s, hasB ? f + 1 : f, c);
+#ifndef B200S_EMU_EXACT_FFT
+		// ---- output spectra of the two blocks -> registers (in flight while the ring is being emitted)
+		float2 ya[G::R3], yb[G::R3];
+		static_for<G::R3>([&](auto itc) {
+			constexpr int it = decltype(itc)::value;
+			ya[it] = YA[tid + 256 * it];
+			yb[it] = YB[tid + 256 * it];
+		});
+#endif
+		emit(tA - emitted);
+#ifdef B200S_EMU_EXACT_FFT // test builds only
+		float *yTimeA = (float *)buf, *yTimeB = yTimeA + B;
+		__syncthreads();
+		if (tid == 0) {
+			emu_exact_inverse(YA, B, o, g.N, yTimeA);
+			if (hasB) emu_exact_inverse(YB, B, o, g.N, yTimeB);
+		}
+		__syncthreads();
+#else
+		// ---- Z'[k]: k = b/2 takes Y[b] (b even), k = K-1-b/2 takes conj(Y[b]) (b odd); natural-order slots
+		static_for<G::R3>([&](auto itc) {
+			constexpr int it = decltype(itc)::value;
+			const int b = tid + 256 * it, hb = b >> 1, k = (b & 1) ? KT - 1 - hb : hb;
+			const float sg = (b & 1) ? -1.f : 1.f;
+			buf[G::slot_in(k)] = make_float4(ya[it].x, yb[it].x, sg * ya[it].y, sg * yb[it].y);
+		});
+		__syncthreads(); // buf complete; the emission above is complete too
+		pair_fft<true, KT>(buf, tw, tid);
+#endif
+		// ---- one sweep over the ring: slot j ahead of the head gets, in the reference's order,
+		//      block A's sample j-addOff, the emission if j < gap, then block B's sample (relative to the new head)
+		// windowed synthesis output sample i of transform `which`: w[i] * 2*Re/Im(z[n2] * conj(pre[n2]))
+		auto contrib = [&](int i, bool second) -> float {
+			const float w = __ldg(x.window + i);
+#ifdef B200S_EMU_EXACT_FFT
+			return fmul((second ? yTimeB : yTimeA)[i], w);
+#else
+			const bool hi = i >= o;
+			const int n2 = hi ? i - o : i - o + KT;
+			const float4 z = buf[G::slot_out(n2)];
+			const float2 p = __ldg(x.pretw + n2);
+			const float re = second ? z.y : z.x, im = second ? z.w : z.z;
+			const float y = hi ? (re * p.x + im * p.y) : (im * p.x - re * p.y);
+			return fmul(2.f * y, w);
+#endif
+		};
+		for (int j = tid; j < P; j += 256) {
+			int p = head + j;
+			if (p >= P) p -= P;
+			float pv = pend[p], wv = wp[p];
+			if (j >= addOff) { // block A (:397-399): i = j - addOff in [0, B)
+				const int i = j - addOff;
+				const float w = __ldg(x.window + i);
+				pv = fadd(pv, contrib(i, false));
+				wv = fadd(wv, fmul(fmul(w, w), fN));
+			}
+			if (hasB) {
+				int i = j - gap - addOff; // block B's sample for this slot, relative to the head after the emission
+				if (j < gap) { // emitted between the blocks (:408-414)
+					out[emitted + j] = fdiv(pv, wv);
+					pv = 0.f;
+					wv = B200S_ALMOST_ZERO;
+					i += P;
+				}
+				if (i >= 0 && i < B) {
+					const float w = __ldg(x.window + i);
+					pv = fadd(pv, contrib(i, true));
+					wv = fadd(wv, fmul(fmul(w, w), fN));
+				}
+			}
+			pend[p] = pv;
+			wp[p] = wv;
+		}
+		if (hasB) {
+			// gap <= P always here?  blocks trigger every H <= B <= P samples; larger gaps cannot occur inside a call
+			head = (head + gap) % P;
+			emitted += gap;
+		}
+		__syncthreads();
+	}
+	emit(x.nOut - emitted);
+	__syncthreads();
+	for (int i = tid; i < P; i += 256) {
+		int p = head + i;
+		if (p >= P) p -= P;
+		gp[i] = pend[p];
+		gw[i] = wp[p];
+	}
+}
+
+static inline size_t smem_analyse2(const Cfg &g) {
+	const int len = g.K == 3072 ? PairGeo<3072>::LEN : PairGeo<2560>::LEN;
+	return sizeof(float4) * len + sizeof(float) * 2 * stage_len(g.B);
+}
+static inline size_t smem_synth2(const Cfg &g) {
+	const int len = g.K == 3072 ? PairGeo<3072>::LEN : PairGeo<2560>::LEN;
+	return sizeof(float4) * len + sizeof(float) * 2 * g.pendLen;
+}
+
+} // namespace b200s

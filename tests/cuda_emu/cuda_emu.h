@@ -8,6 +8,7 @@
 // cannot load it (signalsmith_stretch_b200 only loads the nvcc-built library).  Not a fallback.
 #pragma once
 #include <pthread.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <cmath>
@@ -34,6 +35,7 @@ struct dim3 {
 	dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 
 static thread_local uint3 threadIdx, blockIdx;
 static thread_local dim3 blockDim, gridDim;
@@ -118,6 +120,8 @@ template <typename T>
 static inline T __shfl_down_sync(unsigned, T v, int d) { return emu::shfl_from(v, (emu::t_tid & 31) + d); }
 template <typename T>
 static inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl_from(v, src); }
+template <typename T>
+static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::shfl_from(v, (emu::t_tid & 31) ^ m); }
 static inline int __any_sync(unsigned, int pred) {
 	int r = 0;
 	for (int l = 0; l < 32; ++l) r |= emu::shfl_from(pred ? 1 : 0, l);
@@ -142,6 +146,8 @@ static inline const char *cudaGetErrorString(cudaError_t) { return "emulator err
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }
+enum { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 2; return 0; }
 static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(1, n + 64); return *p ? 0 : 1; }
 static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }

@@ -98,6 +98,44 @@ def test_kernel_logic_bit_exact_vs_oracle(emu_libs, oracle_port, name, cfg, C, r
     assert np.array_equal(y, ref), "max diff %g" % np.abs(y - ref).max()
 
 
+LONG_CALLS = [
+    # (name, configure, channels, out/in, input samples, chunk): blocks per call chosen so that the direct chain
+    # kernel runs with several warps per stream (hand-off ring between warps) and with more than one round
+    ("stereo_0.8x_2warps", lambda o: o.configure(2, 512, 128), 2, 0.8, 9000, 3000),   # 24 blocks: 2 warps of 16
+    ("stereo_0.8x_2rounds", lambda o: o.configure(2, 512, 128), 2, 0.8, 14000, 9000),  # 71 blocks: 4 warps, 2 rounds
+    ("mono_1.25x_3warps", lambda o: o.configure(1, 384, 96), 1, 1.25, 9000, 8000),     # 84 blocks: 3 warps of 32
+]
+
+
+@pytest.mark.parametrize("name,cfg,C,ratio,n,chunk", LONG_CALLS, ids=[c[0] for c in LONG_CALLS])
+def test_long_calls_multi_warp_chain_bit_exact_vs_oracle(emu_libs, oracle_port, name, cfg, C, ratio, n, chunk):
+    x = signals.batch("harmonic", 2, C, n, 48000)
+    g = _emu(emu_libs["exact"], 2)
+    cfg(g)
+    y = signals.run_batch(g, x, ratio, chunk)
+    ref = _oracle_batch(oracle_port, cfg, x, ratio, chunk)
+    assert np.array_equal(y, ref), "max diff %g" % np.abs(y - ref).max()
+
+
+PRESET_CALLS = [
+    # preset sizes run on the paired-FFT kernels (stft2.cuh); with the oracle's FFT swapped in, their staging,
+    # job pairing and fused overlap-add sweep must reproduce the oracle bit for bit
+    ("default_stereo_0.8x", lambda o: o.presetDefault(2, 48000.0), 2, 0.8, 16000, 5760),  # aligned 16-byte staging
+    ("default_mono_1.25x_odd", lambda o: o.presetDefault(1, 48000.0), 1, 1.25, 12000, 4999),  # unaligned chunks, odd block counts
+    ("cheaper_mono_split", lambda o: o.presetCheaper(1, 48000.0), 1, 1.0, 14000, 6000),
+]
+
+
+@pytest.mark.parametrize("name,cfg,C,ratio,n,chunk", PRESET_CALLS, ids=[c[0] for c in PRESET_CALLS])
+def test_preset_pair_kernels_bit_exact_vs_oracle(emu_libs, oracle_port, name, cfg, C, ratio, n, chunk):
+    x = signals.batch("harmonic", 1, C, n, 48000)
+    g = _emu(emu_libs["exact"], 1)
+    cfg(g)
+    y = signals.run_batch(g, x, ratio, chunk)
+    ref = _oracle_batch(oracle_port, cfg, x, ratio, chunk)
+    assert np.array_equal(y, ref), "max diff %g" % np.abs(y - ref).max()
+
+
 def test_api_sequence_bit_exact_vs_oracle(emu_libs, oracle_port):
     """seek / silence bypass / flush / reset / outputSeek / exact through the batched ABI."""
     x = signals.harmonic(6000, 48000)[None]
@@ -151,7 +189,10 @@ def test_shared_memory_fft_accuracy(emu_libs, oracle_port):
     for cfg, C, n in ((lambda o: o.configure(1, 384, 96), 1, 2000),      # K=192 = 3*4^3
                       (lambda o: o.configure(1, 320, 80), 1, 2000),      # K=160 = 5*4^2*2
                       (lambda o: o.configure(1, 256, 64), 1, 2000),      # K=128 = 4^3*2
-                      (lambda o: o.presetDefault(1, 48000.0), 1, 5760 + 1440 * 2)):  # K=3072
+                      (lambda o: o.presetDefault(1, 48000.0), 1, 5760 + 1440 * 2),   # K=3072: paired in-place FFT, mono pairs
+                      (lambda o: o.presetDefault(2, 48000.0), 2, 5760 + 1440 * 3),   # K=3072: channel pairs, odd block count
+                      (lambda o: o.presetCheaper(2, 48000.0), 2, 4800 + 1920 * 3),   # K=2560 = 16*16*10, split computation
+                      (lambda o: o.presetDefault(1, 44100.0), 1, 5292 + 1323 * 2)):  # K=3072 with an odd history length (unaligned staging)
         x = signals.batch("harmonic", 1, C, n, 48000)
         g = _emu(emu_libs["float"], 1)
         cfg(g)
