@@ -1,0 +1,311 @@
+// chain_direct3.cuh -- k_chain_direct3: the frame-wavefront phase prediction (reference :722-804, see
+// the wavefront comment at k_chain in kernels.cuh) for STEREO calls without frequency map / formants,
+// with the two channels of a block processed by PACKED sm_100 arithmetic.
+//
+//   * lane = block (32 blocks of the call per warp, one stream per warp), as in the first generation,
+//     but every per-channel quantity is an f32x2 register pair {channel 0, channel 1}: the preliminary
+//     prediction, the twists and the phase locking of the quieter channel run once per lane for both
+//     channels (FMUL2 / FADD2 / FFMA2).  The packed instructions round each element exactly like their
+//     scalar forms, and every product / sum below is issued in the reference's association order, so
+//     the results are bit-identical to the scalar kernels (multiply-adds are NOT fused, except inside the
+//     correctly-rounded division / square-root sequences, where the scalar code fuses them too).
+//   * To make the pairs free, the analysis kernel writes the spectra of a stereo call channel-interleaved:
+//     one float4 {re0, re1, im0, im1} per bin (k_analyse2 transforms the two channels as one pair anyway),
+//     so the chunk fill is one 16-byte cp.async per (block, bin) and every tile read is one LDS.128 that
+//     lands directly in register pairs.  Band::output rows (Y) stay planar for the synthesis kernel.
+//   * Measured motivation (profiles/r01_v10_ncu_summary.md): the scalar chain kernels are bound by the
+//     number of instructions on each warp's serial stream (311-455 per bin step at ~5-6 cycles per issue);
+//     packing the channels roughly halves that stream.
+#pragma once
+#include <type_traits>
+
+#include "chain_direct.cuh"
+#include "fft2.cuh"
+#include "kernels.cuh"
+
+namespace b200s {
+
+#define CH3_RING 32
+#define CH3_RS 34 // float4 row stride: step reads [k - D*lane][lane] and the fill below are conflict-free (scratch/bank_check3.py)
+
+struct Chain3Tiles {
+	float4 in[CH3_RING][CH3_RS]; // rolling window of each block's interleaved input spectrum, [bin & 31][lane]
+	float4 pvy[CHAIN_CH][CH3_RS]; // previous-input spectrum at the chunk's bins; overwritten by the finals of the same step
+	float4 p0Out[CHAIN_CH];       // lane 0's predecessor block: {c0.re, c0.im, c1.re, c1.im}
+	float2 p0E[CHAIN_CH];         // its Prediction::energy {c0, c1}
+	const float4 *rowIn[32], *rowPv[32];
+	float2 *rowY[32]; // channel 0 row of Band::output; channel 1 row follows K bins later
+};
+
+// ---- packed counterparts of the exact helpers of kernels.cuh (same operations, same order, per element) ----
+#ifdef B200S_EMU
+__device__ __forceinline__ f2 fma2(f2 x, f2 y, f2 z) { return f2{std::fma(x.a, y.a, z.a), std::fma(x.b, y.b, z.b)}; }
+__device__ __forceinline__ f2 rcp_approx2(f2 b) { return f2{1.0f / b.a, 1.0f / b.b}; }
+__device__ __forceinline__ f2 rsqrt_approx2(f2 b) { return f2{1.0f / std::sqrt(b.a), 1.0f / std::sqrt(b.b)}; }
+__device__ __forceinline__ f2 fdivq2(f2 a, f2 b) { return f2{a.a / b.a, a.b / b.b}; }
+__device__ __forceinline__ f2 fsqrtq2(f2 a) { return f2{std::sqrt(a.a), std::sqrt(a.b)}; }
+#else
+__device__ __forceinline__ f2 fma2(f2 x, f2 y, f2 z) {
+	f2 r;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(x.v), "l"(y.v), "l"(z.v));
+	return r;
+}
+__device__ __forceinline__ f2 neg2(f2 a) { return f2_make(-f2_lo(a), -f2_hi(a)); } // folded into operand modifiers by ptxas
+__device__ __forceinline__ f2 fdivq2(f2 a, f2 b) { // fdivq (kernels.cuh) on both elements
+	float r0, r1;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(f2_lo(b)));
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(f2_hi(b)));
+	f2 r = f2_make(r0, r1);
+	const f2 nb = neg2(b);
+	r = fma2(r, fma2(nb, r, f2_make(1.0f, 1.0f)), r);
+	const f2 q = mul2(a, r);
+	return fma2(fma2(nb, q, a), r, q);
+}
+__device__ __forceinline__ f2 fsqrtq2(f2 a) { // fsqrtq (kernels.cuh) on both elements
+	float r0, r1;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(f2_lo(a)));
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(f2_hi(a)));
+	const f2 r = f2_make(r0, r1);
+	const f2 g = mul2(a, r), h = muls(r, 0.5f);
+	const f2 s = fma2(fma2(neg2(g), g, a), h, g);
+	return f2_make(f2_lo(a) == 0.f ? 0.f : f2_lo(s), f2_hi(a) == 0.f ? 0.f : f2_hi(s));
+}
+#endif
+__device__ __forceinline__ f2 sel_f2(bool p, f2 a) { return f2_make(p ? f2_lo(a) : 0.f, p ? f2_hi(a) : 0.f); }
+__device__ __forceinline__ c2 sel_c2(bool p, c2 a) { return c2{sel_f2(p, a.re), sel_f2(p, a.im)}; }
+// xmul: a * b, both packed
+__device__ __forceinline__ c2 xmul2(c2 a, c2 b) {
+	return c2{mul2(a.re, b.re) - mul2(a.im, b.im), mul2(a.re, b.im) + mul2(a.im, b.re)};
+}
+// xmul with a scalar complex factor on the right (rotation): a * r
+__device__ __forceinline__ c2 xmul2s(c2 a, float2 r) {
+	return c2{muls(a.re, r.x) - muls(a.im, r.y), muls(a.re, r.y) + muls(a.im, r.x)};
+}
+// xmulc: a * conj(b) in the scalar helper's operand order (b.x*a.x + b.y*a.y, b.x*a.y - b.y*a.x)
+__device__ __forceinline__ c2 xmulc2(c2 a, c2 b) {
+	return c2{mul2(b.re, a.re) + mul2(b.im, a.im), mul2(b.re, a.im) - mul2(b.im, a.re)};
+}
+__device__ __forceinline__ f2 xnorm2(c2 a) { return mul2(a.re, a.re) + mul2(a.im, a.im); }
+// low + (high - low)*frac, frac common to both channels
+__device__ __forceinline__ c2 xlerp2p(c2 lo, c2 hi, float fr) {
+	return c2{lo.re + muls(hi.re - lo.re, fr), lo.im + muls(hi.im - lo.im, fr)};
+}
+// Prediction::makeOutput (:596-603) for both channels
+__device__ __forceinline__ c2 make_output_q2(c2 phase, f2 energy, c2 input) {
+	const f2 pn = xnorm2(phase);
+	const bool w0 = f2_lo(pn) <= B200S_NOISE_FLOOR, w1 = f2_hi(pn) <= B200S_NOISE_FLOOR;
+	const f2 pni = xnorm2(input) + f2_make(B200S_NOISE_FLOOR, B200S_NOISE_FLOOR);
+	const c2 ph = c2{f2_make(w0 ? f2_lo(input.re) : f2_lo(phase.re), w1 ? f2_hi(input.re) : f2_hi(phase.re)),
+	                 f2_make(w0 ? f2_lo(input.im) : f2_lo(phase.im), w1 ? f2_hi(input.im) : f2_hi(phase.im))};
+	const f2 pn2 = f2_make(w0 ? f2_lo(pni) : f2_lo(pn), w1 ? f2_hi(pni) : f2_hi(pn));
+	const f2 g = fsqrtq2(fdivq2(energy, pn2));
+	return c2{mul2(ph.re, g), mul2(ph.im, g)};
+}
+__device__ __forceinline__ c2 ld_c2s(const float4 *p) { // shared / global float4 {re0, re1, im0, im1}
+	const float4 v = *p;
+	return c2{f2_make(v.x, v.y), f2_make(v.z, v.w)};
+}
+__device__ __forceinline__ float2 pick(bool second, c2 a) { // one channel of a packed complex
+	return make_float2(second ? f2_hi(a.re) : f2_lo(a.re), second ? f2_hi(a.im) : f2_lo(a.im));
+}
+
+template <int LT>
+__global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
+	const Cfg &g = x.cfg;
+	const int K = g.K;
+	B200S_DYN_SHARED
+	const int lane = threadIdx.x & 31;
+	const int s = x.sBase + blockIdx.x;
+	const Call cl = x.call[s];
+	if (cl.nFrames == 0) return;
+	constexpr int D = LT + 1;
+	Chain3Tiles &U = *(Chain3Tiles *)dyn_smem;
+	// chunk fill: lane -> (bin offset, row within a group of 4); a quarter-warp covers 4 bins (64 B) of 2 rows
+	const int fillI = (lane & 3) | (((lane >> 3) & 1) << 2), fillF = ((lane >> 2) & 1) | (((lane >> 4) & 1) << 1);
+	const float2 rot0 = x.rot0, rotStep = x.rotStep;
+
+	for (int base = 0; base < cl.nFrames; base += 32) {
+		__syncwarp();
+		const int f = base + lane;
+		const bool active = f < cl.nFrames;
+		const Frame fr = x.frames[(size_t)s * x.maxFrames + (active ? f : base)];
+		const bool rotOn = fr.flags & FR_NEW_SPECTRUM;
+		const int nAct = min(32, cl.nFrames - base);
+		const bool carryE = active && (lane == 31 || f == cl.nFrames - 1); // Prediction::energy needed later
+		const float tf = fmaxf(fr.timeFactor, 1.0f / B200S_MAX_CLEAN_STRETCH); // :638
+		const float longTf = fmul((float)LT, tf);
+		const bool farAny = __any_sync(0xffffffffu, active && longTf > (float)(CH3_RING - CHAIN_CH - 3));
+		const float2 *prevOut[2];
+		const float *prevE[2];
+#pragma unroll
+		for (int c = 0; c < 2; ++c) {
+			prevOut[c] = base == 0 ? x.stOut + ((size_t)s * 2 + c) * K : x.Y + coef_off(x, s, base - 1, c);
+			prevE[c] = base == 0 ? x.stPredE + ((size_t)s * 2 + c) * K : x.cE + coef_off(x, s, base - 1, c);
+		}
+		const float4 *myIn = il_row(x, s, fr.inSlot);
+		float *myE = x.cE + coef_off(x, s, active ? f : base, 0); // channel 1: + K
+		U.rowIn[lane] = myIn;
+		U.rowPv[lane] = il_row(x, s, fr.prevSlot);
+		U.rowY[lane] = x.Y + coef_off(x, s, active ? f : base, 0);
+		__syncwarp();
+		// register FIFOs (channel pairs); at the start of a step (q = prelim bin, b = q - L = final bin):
+		//   pre/eF/t2F/inF[i] <-> prelim output / energy / long twist / input at bin b+i
+		//   oh[i] <-> final output at bin b-1-i;   t1P <-> short twist at bin b
+		const f2 z2 = f2_make(0.f, 0.f);
+		const c2 zc = c2{z2, z2};
+		c2 oh[LT], pre[LT], t2F[LT], inF[LT], t1P = zc, lastFinal = zc;
+		f2 eF[LT], lastE = z2;
+#pragma unroll
+		for (int i = 0; i < LT; ++i) {
+			oh[i] = pre[i] = t2F[i] = inF[i] = zc;
+			eF[i] = z2;
+		}
+		float2 rotq = rotOn ? rot0 : make_float2(1.f, 0.f); // rot[q] by the reference's float recurrence (:647-655)
+		const float2 rotS = rotOn ? rotStep : make_float2(1.f, 0.f);
+		const int steps = K + LT + D * (nAct - 1);
+		for (int k0 = 0; k0 < steps; k0 += CHAIN_CH) {
+			// ---------------- stage the chunk: 8 new bins per block, both channels per 16-byte copy ----------------
+#pragma unroll
+			for (int it = 0; it < 8; ++it) {
+				const int fl = fillF + 4 * it;
+				const int q = k0 + fillI - D * fl;
+				if (base + fl < cl.nFrames && (unsigned)q < (unsigned)K) {
+					cp_async16(&U.in[q & (CH3_RING - 1)][fl], U.rowIn[fl] + q);
+					cp_async16(&U.pvy[fillI][fl], U.rowPv[fl] + q);
+				}
+			}
+			if (lane < 2 * CHAIN_CH) { // lane 0's predecessor: planar state / previous group rows -> {c0, c1} slots
+				const int qq = k0 + (lane >> 1), c = lane & 1;
+				if (qq < K) {
+					cp_async8((float2 *)&U.p0Out[lane >> 1] + c, (c ? prevOut[1] : prevOut[0]) + qq);
+					cp_async4((float *)&U.p0E[lane >> 1] + c, (c ? prevE[1] : prevE[0]) + qq);
+				}
+			}
+			cp_async_wait_all();
+			__syncwarp();
+			// ---------------- CHAIN_CH steps ----------------
+			auto step = [&](const int i, auto farTag) {
+				constexpr bool FAR = decltype(farTag)::value;
+				const int q = k0 + i - D * lane;
+				const int b = q - LT;
+				const bool qIn = active && (unsigned)q < (unsigned)K;
+				const bool bIn = active && (unsigned)b < (unsigned)K;
+				// the twists need input interpolated at q - L*tf and (b+1) - tf  (:750,:757)
+				const float i2 = fsub((float)q, longTf);
+				const int l2 = (int)floorf(i2);
+				const float f2s = fsub(i2, (float)l2);
+				const float i1 = fsub((float)(b + 1), tf);
+				const int l1 = (int)floorf(i1);
+				const float f1s = fsub(i1, (float)l1);
+				// previous block's final output / energy at bin q: finalised by lane-1 in the last step
+				c2 ro;
+				f2 re;
+				{
+					const float a0 = __shfl_up_sync(0xffffffffu, f2_lo(lastFinal.re), 1), a1 = __shfl_up_sync(0xffffffffu, f2_hi(lastFinal.re), 1);
+					const float b0 = __shfl_up_sync(0xffffffffu, f2_lo(lastFinal.im), 1), b1 = __shfl_up_sync(0xffffffffu, f2_hi(lastFinal.im), 1);
+					const float e0 = __shfl_up_sync(0xffffffffu, f2_lo(lastE), 1), e1 = __shfl_up_sync(0xffffffffu, f2_hi(lastE), 1);
+					const float4 p0 = U.p0Out[i];
+					const float2 p0e = U.p0E[i];
+					const bool first = lane == 0;
+					ro = c2{f2_make(first ? p0.x : a0, first ? p0.z : a1), f2_make(first ? p0.y : b0, first ? p0.w : b1)};
+					re = f2_make(first ? p0e.x : e0, first ? p0e.y : e1);
+				}
+				const c2 inq = ld_c2s(&U.in[q & (CH3_RING - 1)][lane]);
+				c2 pv = ld_c2s(&U.pvy[i][lane]);
+				c2 lo2, hi2, lo1, hi1;
+				if constexpr (!FAR) {
+					lo2 = sel_c2(l2 >= 0, ld_c2s(&U.in[l2 & (CH3_RING - 1)][lane]));
+					hi2 = sel_c2(l2 >= -1, ld_c2s(&U.in[(l2 + 1) & (CH3_RING - 1)][lane]));
+					lo1 = sel_c2(l1 >= 0, ld_c2s(&U.in[l1 & (CH3_RING - 1)][lane]));
+					hi1 = sel_c2(l1 >= -1, ld_c2s(&U.in[(l1 + 1) & (CH3_RING - 1)][lane]));
+				} else { // extreme stretch (> 2x): gather straight from the spectrum row
+					lo2 = (l2 < 0 || l2 >= K) ? zc : ld_c2s(myIn + l2);
+					hi2 = (l2 + 1 < 0 || l2 + 1 >= K) ? zc : ld_c2s(myIn + l2 + 1);
+					lo1 = (l1 < 0 || l1 >= K) ? zc : ld_c2s(myIn + l1);
+					hi1 = (l1 + 1 < 0 || l1 + 1 >= K) ? zc : ld_c2s(myIn + l1 + 1);
+				}
+				pv = xmul2s(pv, rotq); // :653-654 rotate Band::output and Band::prevInput by one interval
+				ro = xmul2s(ro, rotq);
+				const f2 e = xnorm2(inq);                       // :679 (identity map: energy = |input|^2)
+				const c2 ph0 = xmul2(ro, xmulc2(inq, pv));      // :714-715
+				const f2 den = f2_make(fmaxf(f2_lo(re), f2_lo(e)), fmaxf(f2_hi(re), f2_hi(e))) + f2_make(B200S_NOISE_FLOOR, B200S_NOISE_FLOOR);
+				const c2 newPre = sel_c2(qIn, c2{fdivq2(ph0.re, den), fdivq2(ph0.im, den)}); // :716
+				const f2 newE = sel_f2(qIn, e);
+				const c2 newIn = sel_c2(qIn, inq);
+				const c2 newT2 = sel_c2(qIn, xmulc2(inq, xlerp2p(lo2, hi2, f2s))); // long twist at q (:758)
+				// short twist at b+1 (:751,:771): Prediction::input[b+1] is inF[1] before the shift
+				const c2 t1N = xmulc2(LT > 1 ? inF[LT > 1 ? 1 : 0] : newIn, xlerp2p(lo1, hi1, f1s));
+				{
+					const float2 rn = xmul(rotq, rotS);
+					rotq = make_float2(q >= 0 ? rn.x : rotq.x, q >= 0 ? rn.y : rotq.y);
+				}
+				// ---- FIFO rotation (pure renaming after unrolling): what falls out belongs to bin b
+				const f2 eB = eF[0];
+				const c2 t2B = t2F[0], inB = inF[0];
+#pragma unroll
+				for (int u = 0; u + 1 < LT; ++u) {
+					pre[u] = pre[u + 1];
+					eF[u] = eF[u + 1];
+					t2F[u] = t2F[u + 1];
+					inF[u] = inF[u + 1];
+				}
+				pre[LT - 1] = newPre;
+				eF[LT - 1] = newE;
+				t2F[LT - 1] = newT2;
+				inF[LT - 1] = newIn;
+				// ---- main prediction at bin b (:727-800): the louder channel (first on ties, :733) leads
+				const bool m = f2_hi(eB) > f2_lo(eB);
+				const float maxE = m ? f2_hi(eB) : f2_lo(eB);
+				const float2 oh1 = pick(m, oh[0]), ohL = pick(m, oh[LT - 1]), pr1 = pick(m, pre[0]), prL = pick(m, pre[LT - 1]);
+				const float2 t1b = pick(m, t1P), t2b = pick(m, t2B), t1n = pick(m, t1N), t2n = pick(m, t2F[LT - 1]), pinM = pick(m, inB);
+				float2 phase = make_float2(0.f, 0.f);
+				phase = xadd(phase, sel2(b > 0, xmul(oh1, t1b)));         // :754
+				phase = xadd(phase, sel2(b >= LT, xmul(ohL, t2b)));       // :761
+				phase = xadd(phase, sel2(b < K - 1, xmulc(pr1, t1n)));    // :774
+				phase = xadd(phase, sel2(b < K - LT, xmulc(prL, t2n)));   // :784
+				const float2 outM = make_output_q(phase, maxE, pinM);     // :788
+				// the other channel is locked in phase (:791-799); computed for both, the leader keeps outM
+				//   cph = xmul(outM, xmulc(inB_c, pinM)), operand order of the scalar helpers
+				const c2 tw = c2{muls(inB.re, pinM.x) + muls(inB.im, pinM.y), muls(inB.im, pinM.x) - muls(inB.re, pinM.y)};
+				const c2 cph = c2{muls(tw.re, outM.x) - muls(tw.im, outM.y), muls(tw.im, outM.x) + muls(tw.re, outM.y)};
+				const c2 other = make_output_q2(cph, eB, inB);
+				const c2 oc = c2{f2_make(m ? f2_lo(other.re) : outM.x, m ? outM.x : f2_hi(other.re)),
+				                 f2_make(m ? f2_lo(other.im) : outM.y, m ? outM.y : f2_hi(other.im))};
+				// unconditional: out-of-range steps only produce values that every consumer masks
+#pragma unroll
+				for (int u = LT - 1; u > 0; --u) oh[u] = oh[u - 1];
+				oh[0] = oc;
+				lastFinal = oc;
+				lastE = eB;
+				t1P = t1N;
+				if (carryE && bIn) {
+					myE[b] = f2_lo(eB);
+					myE[K + b] = f2_hi(eB);
+				}
+				U.pvy[i][lane] = make_float4(f2_lo(oc.re), f2_hi(oc.re), f2_lo(oc.im), f2_hi(oc.im));
+			};
+			if (!farAny) { // fully unrolled, branch-free: one basic block the scheduler can interleave
+#pragma unroll
+				for (int i = 0; i < CHAIN_CH; ++i) step(i, std::false_type{});
+			} else {
+#pragma unroll 1
+				for (int i = 0; i < CHAIN_CH; ++i) step(i, std::true_type{});
+			}
+			__syncwarp();
+			// ---------------- write the chunk's finals back: planar Band::output rows, 32 B per row and quarter-warp ----------------
+#pragma unroll
+			for (int it = 0; it < 8; ++it) {
+				const int fl = fillF + 4 * it;
+				const int b = k0 + fillI - D * fl - LT;
+				if (base + fl < cl.nFrames && (unsigned)b < (unsigned)K) {
+					const float4 v = U.pvy[fillI][fl];
+					U.rowY[fl][b] = make_float2(v.x, v.z);
+					U.rowY[fl][K + b] = make_float2(v.y, v.w);
+				}
+			}
+			__syncwarp();
+		}
+	}
+}
+
+} // namespace b200s

@@ -110,6 +110,10 @@ struct Ctx {
 	float *pend, *pendWp;
 	float2 *stIn, *stPrev, *stOut;
 	float *stPredE;
+	// stereo direct path: spectra are channel-interleaved float4 {re0, re1, im0, im1} per bin (chain_direct3.cuh);
+	// stIl [S][2][K] holds such copies of stIn / stPrev, made by k_plan at the start of the call
+	float4 *stIl;
+	int specIl;
 	// call scratch
 	int maxFrames;
 	Frame *frames; // [S][maxFrames]

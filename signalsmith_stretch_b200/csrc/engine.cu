@@ -20,6 +20,7 @@
 #include "chain_direct.cuh"
 #include "chain_direct2.cuh"
 #include "stft2.cuh"
+#include "chain_direct3.cuh"
 
 using namespace b200s;
 
@@ -34,10 +35,11 @@ struct b200s_engine {
 	cudaStream_t stream = 0;
 	bool ownStream = false;
 	// sub-batch pipeline: process() splits the batch over these prioritised streams (see process_impl)
-	static const int kMaxSub = 4;
+	static const int kMaxSub = 8;
 	int nSub = 1, maxSub = 1;
-	cudaStream_t subStream[kMaxSub] = {0, 0, 0, 0};
-	cudaEvent_t evBegin = 0, evSubDone[kMaxSub] = {0, 0, 0, 0};
+	cudaStream_t subStream[kMaxSub] = {0, 0, 0, 0, 0, 0, 0, 0};
+	cudaEvent_t evBegin = 0, evSubDone[kMaxSub] = {0, 0, 0, 0, 0, 0, 0, 0};
+	int nHostParts = 4; // host-buffer API: stream groups whose H2D copy / kernels / D2H copy are pipelined
 	cudaEvent_t evStart = 0, evStop = 0;
 	long long launches = 0;
 	std::string err;
@@ -58,6 +60,7 @@ struct b200s_engine {
 	float *dPend = 0, *dPendWp = 0;
 	float2 *dStIn = 0, *dStPrev = 0, *dStOut = 0;
 	float *dStPredE = 0;
+	float4 *dStIl = 0;
 	// call scratch
 	int maxFrames = 0;
 	Frame *dFrames = 0;
@@ -109,7 +112,7 @@ static void dfree(T *&p) {
 static void free_all(b200s_engine *e) {
 	dfree(e->dWindow); dfree(e->dWinProd); dfree(e->dWpReset); dfree(e->dRot); dfree(e->dTwiddle); dfree(e->dPretw);
 	dfree(e->dSched); dfree(e->dHist[0]); dfree(e->dHist[1]); dfree(e->dPend); dfree(e->dPendWp);
-	dfree(e->dStIn); dfree(e->dStPrev); dfree(e->dStOut); dfree(e->dStPredE);
+	dfree(e->dStIn); dfree(e->dStPrev); dfree(e->dStOut); dfree(e->dStPredE); dfree(e->dStIl);
 	dfree(e->dFrames); dfree(e->dCall); dfree(e->dJobs); dfree(e->dSpec); dfree(e->dY); dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dE);
 	dfree(e->dIn); dfree(e->dOut); dfree(e->dZero); dfree(e->dTmp);
 	e->maxFrames = 0;
@@ -129,7 +132,7 @@ static Ctx make_ctx(b200s_engine *e) {
 	x.sched = e->dSched;
 	x.histCur = e->dHist[e->histCur]; x.histNext = e->dHist[e->histCur ^ 1];
 	x.pend = e->dPend; x.pendWp = e->dPendWp;
-	x.stIn = e->dStIn; x.stPrev = e->dStPrev; x.stOut = e->dStOut; x.stPredE = e->dStPredE;
+	x.stIn = e->dStIn; x.stPrev = e->dStPrev; x.stOut = e->dStOut; x.stPredE = e->dStPredE; x.stIl = e->dStIl;
 	x.maxFrames = e->maxFrames;
 	x.sBase = 0; x.sCount = e->S;
 	x.frames = e->dFrames; x.call = e->dCall; x.jobs = e->dJobs;
@@ -224,10 +227,29 @@ static int chain2_warps(const Cfg &g, int nOut) {
 	const int blocks = (nOut + g.H - 1) / g.H, bpw = 32 / g.C;
 	return std::max(1, std::min(CH2_MAXW, (blocks + bpw - 1) / bpw));
 }
-static bool use_chain_v1() {
-	static int v = -1;
-	if (v < 0) v = getenv("B200S_CHAIN_V1") ? 1 : 0; // A/B switch for profiling the first-generation kernel
-	return v == 1;
+// which direct chain kernel: 3 = packed stereo (chain_direct3.cuh, needs the paired analysis kernel),
+// 2 = lane-per-(block,channel) multi-warp (chain_direct2.cuh), 1 = first generation; B200S_CHAIN_V overrides (A/B profiling)
+static int chain_version(const Cfg &g) {
+	static int env = -1;
+	if (env < 0) {
+		const char *v = getenv("B200S_CHAIN_V");
+		env = v ? atoi(v) : 0;
+	}
+	int want = env ? env : 3;
+	if (want == 3 && !(g.C == 2 && use_pair_fft(g))) want = 2;
+	return want;
+}
+static ChainKernel chain3_kernel(const Cfg &g) {
+	switch (g.L) {
+	case 1: return k_chain_direct3<1>;
+	case 2: return k_chain_direct3<2>;
+	case 3: return k_chain_direct3<3>;
+	case 4: return k_chain_direct3<4>;
+	case 5: return k_chain_direct3<5>;
+	case 6: return k_chain_direct3<6>;
+	case 7: return k_chain_direct3<7>;
+	default: return k_chain_direct3<8>;
+	}
 }
 static ChainKernel chain_kernel(const Cfg &g, bool direct) {
 	return g.C == 1 ? chain_kernel_for<1>(g.L, direct) : chain_kernel_for<2>(g.L, direct);
@@ -375,6 +397,7 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	if ((rc = dalloc(e, &e->dStPrev, SC * g.K))) return rc;
 	if ((rc = dalloc(e, &e->dStOut, SC * g.K))) return rc;
 	if ((rc = dalloc(e, &e->dStPredE, SC * g.K))) return rc;
+	if ((rc = dalloc(e, &e->dStIl, g.C == 2 ? (size_t)g.S * 2 * g.K : 1))) return rc;
 	if ((rc = dalloc(e, &e->dCall, g.S))) return rc;
 	CK(cudaMemset(e->dStPredE, 0, sizeof(float) * SC * g.K));
 	CK(cudaMemset(e->dHist[1], 0, sizeof(float) * SC * g.histLen));
@@ -444,8 +467,12 @@ static int ensure_buf(b200s_engine *e, float **p, size_t *cap, size_t n, bool ze
 }
 
 // process() on device buffers with explicit strides (floats between channels / streams)
+// hIn / hOut (host-buffer API only): packed [S][C][n] host arrays mirrored by dIn / dOut; each stream group
+// then copies its own slab in, runs its kernels and copies its slab out on its own CUDA stream, so that the
+// PCIe transfers of one group overlap the kernels of the others.
 static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, long long inStreamStride, int nIn,
-                        float *dOut, int outChanStride, long long outStreamStride, int nOut) {
+                        float *dOut, int outChanStride, long long outStreamStride, int nOut,
+                        const float *hIn = nullptr, float *hOut = nullptr) {
 	const Cfg &g = e->cfg;
 	if (nIn < 0 || nOut < 0) {
 		e->err = "process: negative sample count";
@@ -464,14 +491,20 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	// sub-batch 1 is still in its FFT kernel, and so on: the latency-bound wavefront kernel and the
 	// throughput-bound FFT kernels share the SMs instead of taking turns.  Per-kernel profiling
 	// (b200s_profile_begin) runs unsplit on the main stream so that the event pairs time one kernel each.
-	const int nSub = (e->profiling || e->nSub <= 1 || g.S < 64) ? 1 : e->nSub;
+	const bool hostIO = hIn || hOut;
+	const int wantSub = hostIO ? e->nHostParts : e->nSub;
+	const int nSub = (e->profiling || wantSub <= 1 || g.S < 64) ? 1 : std::min(wantSub, e->maxSub);
 	if (nSub > 1) CK(cudaEventRecord(e->evBegin, e->stream));
 	const bool plain = !(e->prm.mapN > 0 || e->prm.freqMultiplier != 1.0f) && e->prm.formantMultiplier == 1.0f;
+	const int chainV = chain_version(g);
+	x.specIl = (plain && chainV == 3) ? 1 : 0;
 	for (int sub = 0; sub < nSub; ++sub) {
 		cudaStream_t st = nSub > 1 ? e->subStream[sub] : e->stream;
 		if (nSub > 1) CK(cudaStreamWaitEvent(st, e->evBegin, 0));
 		x.sBase = (int)((long long)g.S * sub / nSub);
 		x.sCount = (int)((long long)g.S * (sub + 1) / nSub) - x.sBase;
+		if (hIn && nIn > 0)
+			CK(cudaMemcpyAsync((float *)dIn + (size_t)x.sBase * g.C * nIn, hIn + (size_t)x.sBase * g.C * nIn, sizeof(float) * (size_t)x.sCount * g.C * nIn, cudaMemcpyHostToDevice, st));
 		{ // (profiling implies nSub == 1, i.e. st == e->stream, which is where PROF() records its events)
 			PROF(PK_PLAN, B200S_LAUNCH(k_plan, dim3(x.sCount), dim3(kThreads), 0, st, x));
 			if (F > 0) {
@@ -486,7 +519,9 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 				// Pure time-stretch (no frequency map, no formants): the chain forms its terms directly from
 				// the spectra and k_prep is skipped; otherwise k_prep produces the coefficient arrays.
 				if (!plain) PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g), st, x));
-				if (plain && !use_chain_v1()) {
+				if (plain && chainV == 3) {
+					PROF(PK_CHAIN, B200S_LAUNCH(chain3_kernel(g), dim3(x.sCount), dim3(32), sizeof(Chain3Tiles), st, x));
+				} else if (plain && chainV == 2) {
 					const int W = chain2_warps(g, nOut);
 					ChainKernel kc = chain2_kernel(g);
 					PROF(PK_CHAIN, B200S_LAUNCH(kc, dim3(x.sCount), dim3(32 * W), smem_chain2(g.C, W), st, x));
@@ -504,6 +539,8 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 			}
 			PROF(PK_COMMIT, B200S_LAUNCH(k_commit, dim3(x.sCount), dim3(kThreads), 0, st, x));
 		}
+		if (hOut && nOut > 0)
+			CK(cudaMemcpyAsync(hOut + (size_t)x.sBase * g.C * nOut, dOut + (size_t)x.sBase * g.C * nOut, sizeof(float) * (size_t)x.sCount * g.C * nOut, cudaMemcpyDeviceToHost, st));
 		if (nSub > 1) {
 			CK(cudaEventRecord(e->evSubDone[sub], st));
 			CK(cudaStreamWaitEvent(e->stream, e->evSubDone[sub], 0));
@@ -566,7 +603,7 @@ static int stage_in(b200s_engine *e, const float *in, int n) {
 	size_t cnt = (size_t)e->cfg.S * e->cfg.C * std::max(n, 1);
 	int rc;
 	if ((rc = ensure_buf(e, &e->dIn, &e->inCap, cnt, false))) return rc;
-	if (n > 0) CK(cudaMemcpyAsync(e->dIn, in, sizeof(float) * (size_t)e->cfg.S * e->cfg.C * n, cudaMemcpyHostToDevice, e->stream));
+	if (n > 0 && in) CK(cudaMemcpyAsync(e->dIn, in, sizeof(float) * (size_t)e->cfg.S * e->cfg.C * n, cudaMemcpyHostToDevice, e->stream));
 	return 0;
 }
 static int stage_out(b200s_engine *e, int n) {
@@ -628,6 +665,7 @@ int b200s_create(int batch, long seed, int device, b200s_engine **out) {
 		// batches large enough to oversubscribe the SMs; b200s_set_sub_batches() turns it on.
 		e->nSub = 1;
 		e->maxSub = ok ? b200s_engine::kMaxSub : 1;
+		if (const char *hp = getenv("B200S_HOST_PARTS")) e->nHostParts = std::max(1, atoi(hp)); // tuning knob of the host-buffer pipeline
 	}
 	*out = e;
 	return 0;
@@ -792,10 +830,11 @@ int b200s_process(b200s_engine *e, const float *in, int nIn, float *out, int nOu
 	NEED_CFG();
 	int rc;
 	if ((rc = check_formant_support(e))) return rc;
-	if ((rc = stage_in(e, in, nIn))) return rc;
+	if ((rc = stage_in(e, nullptr, nIn))) return rc; // capacity only: the copies are issued per stream group
 	if ((rc = stage_out(e, nOut))) return rc;
-	if ((rc = process_impl(e, e->dIn, nIn, (long long)e->cfg.C * nIn, nIn, e->dOut, nOut, (long long)e->cfg.C * nOut, nOut))) return rc;
-	return fetch_out(e, out, nOut);
+	if ((rc = process_impl(e, e->dIn, nIn, (long long)e->cfg.C * nIn, nIn, e->dOut, nOut, (long long)e->cfg.C * nOut, nOut, in, out))) return rc;
+	CK(cudaStreamSynchronize(e->stream));
+	return 0;
 }
 int b200s_flush(b200s_engine *e, float *out, int nOut, float rate) {
 	NEED_CFG();

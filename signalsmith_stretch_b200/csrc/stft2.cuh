@@ -99,11 +99,17 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 			const int shA = x.inAligned ? (cur.a.start & 3) : 0, shB = x.inAligned ? (cur.b.start & 3) : 0;
 			if (tid == 0) {
 				float *xw = (float *)buf;
+				// interleaved mode: transform into scratch rows (cPI is unused on the direct path), then interleave
+				float2 *tA = x.specIl ? x.cPI + coef_off(x, cur.s, 0, 0) : dstA, *tB = x.specIl ? tA + KT : dstB;
 				for (int i = 0; i < B; ++i) xw[i] = fmul(stA[i + shA], x.window[i]);
-				emu_exact_forward(xw, B, o, 2 * KT, dstA);
+				emu_exact_forward(xw, B, o, 2 * KT, tA);
 				if (cur.hasB) {
 					for (int i = 0; i < B; ++i) xw[i] = fmul(stB[i + shB], x.window[i]);
-					emu_exact_forward(xw, B, o, 2 * KT, dstB);
+					emu_exact_forward(xw, B, o, 2 * KT, tB);
+				}
+				if (x.specIl) {
+					float4 *d4 = (float4 *)x.spec + ((size_t)cur.s * 2 * x.maxFrames + (cur.a.row >> 1)) * g.K;
+					for (int b = 0; b < KT; ++b) d4[b] = make_float4(tA[b].x, tB[b].x, tA[b].y, tB[b].y);
 				}
 			}
 			__syncthreads();
@@ -140,14 +146,20 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 		}
 		pair_fft<false, KT>(buf, tw, tid);
 		{ // ---- unpack: bin b = Z[b/2] (b even) or conj(Z[K-1-b/2]) (b odd), Z digit-reversed in buf
-			const bool hasB = cur.hasB;
+			const bool hasB = cur.hasB, il = x.specIl;
+			// stereo direct path: the pair is (channel 0, channel 1) of one analysis and is stored interleaved
+			float4 *dst4 = (float4 *)x.spec + ((size_t)cur.s * 2 * x.maxFrames + (cur.a.row >> 1)) * g.K;
 			static_for<G::R3>([&](auto itc) {
 				const int b = tid + 256 * decltype(itc)::value;
 				const int hb = b >> 1, k = (b & 1) ? KT - 1 - hb : hb;
 				const float4 z = buf[G::slot_out(k)];
 				const float sg = (b & 1) ? -1.f : 1.f;
-				dstA[b] = make_float2(z.x, sg * z.z);
-				if (hasB) dstB[b] = make_float2(z.y, sg * z.w);
+				if (il) {
+					dst4[b] = make_float4(z.x, z.y, sg * z.z, sg * z.w);
+				} else {
+					dstA[b] = make_float2(z.x, sg * z.z);
+					if (hasB) dstB[b] = make_float2(z.y, sg * z.w);
+				}
 			});
 		}
 		item = nitem;
