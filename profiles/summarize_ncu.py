@@ -20,6 +20,11 @@ KEYS = [
     ("lts__t_sector_hit_rate.pct", "L2 hit %"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe busy %"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe %"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1/shared wavefronts % of peak"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
 ]
 
 
@@ -52,6 +57,16 @@ def full(path):
             if key in hdr:
                 j = hdr.index(key)
                 out.append("| %s (`%s`) | %s | %s |" % (label, key, r[j], units[j]))
+        stalls = []
+        for j, h in enumerate(hdr):
+            if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and "not_issued" not in h:
+                try:
+                    stalls.append((float(r[j].replace(",", "")), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
+                except ValueError:
+                    pass
+        stalls.sort(reverse=True)
+        out.append("")
+        out.append("warp stall cycles per issued instruction (top): " + ", ".join("%s %.2f" % (k, v) for v, k in stalls[:7]))
         out.append("")
     return "\n".join(out)
 
@@ -59,7 +74,7 @@ def full(path):
 if __name__ == "__main__":
     tag = sys.argv[1]
     print("# ncu summary %s\n" % tag)
-    for a in sys.argv[2:]:
+    for a in [a for a in sys.argv[2:] if a]:
         if a.endswith(".csv"):
             print("## launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare shares)\n")
             print(launches(a) + "\n")

@@ -9,14 +9,16 @@
 //     pair, twiddles as broadcast scalar operands), every shared-memory access is one LDS.128 /
 //     STS.128, and the twiddle / address arithmetic is shared by the two transforms: about half the
 //     issue slots per transform of a scalar FFT (measured: the scalar kernels were issue-bound).
-//   * IN-PLACE decimation in frequency: a pass reads R elements into registers, does the radix-R
-//     butterfly and writes the results to the SAME R slots, so one buffer (K float4 + padding)
-//     suffices and no pass needs a barrier between its loads and stores.  Three passes 16 x 16 x R3
-//     (R3 = 12 or 10).  The result comes out digit-reversed; the consumers index it accordingly:
-//         input  n = n1*M1 + n2*R3 + n3   lives at slot  n1*P1 + n2*P2 + n3      (M1 = 16*R3)
-//         output k = k1 + 16*k2 + 256*k3  lives at slot  k1*P1 + k2*P2 + k3
-//   * Slot strides P2 = R3+1 and P1 = 16*P2+1 are odd, and in every pass the lanes of a warp walk a
-//     digit whose stride is odd, so the 128-bit accesses are bank-conflict free.
+//   * IN-PLACE: a pass reads R elements into registers, does the radix-R butterfly and writes the
+//     results to the SAME R slots, so one buffer (K float4 + padding) suffices and no pass needs a
+//     barrier between its loads and stores.  Three passes 16 x 16 x R3 (R3 = 12 or 10).
+//   * The first and the last pass are FUSED with the caller's data movement, which removes two of the
+//     six shared-memory sweeps (the kernels were bound by shared-memory wavefronts and issue slots):
+//       - analysis: decimation in time.  The thread that windows and pre-twiddles its R3 input samples
+//         does the first (radix R3) butterfly on them in registers; the last radix-16 pass leaves the
+//         spectrum in registers in natural order and the caller stores it to HBM directly.
+//       - synthesis: decimation in frequency.  The first radix-16 pass takes its inputs straight from
+//         HBM; the result ends digit-reversed in the buffer, where the overlap-add sweep indexes it.
 //   * Inter-pass twiddles: w, w^2, w^4, w^8 of the thread's (fixed) item are kept in registers for the
 //     lifetime of the CTA, the other powers are products of at most three of them.
 // No cuFFT, no tensor cores.  Generic sizes use the scalar Stockham FFT of fft.cuh.
@@ -204,22 +206,22 @@ template <bool INV> struct PairDFT<12, INV> : PairComposite<4, 3, INV> {};
 template <bool INV> struct PairDFT<16, INV> : PairComposite<4, 4, INV> {};
 
 // ---- geometry of the paired in-place FFT ----
+// K = 16 * 16 * R3 points in one buffer of LEN float4 slots; a slot address is d1*P1 + d2*P2 + d3 for digits
+// (d1, d2 in [0,16), d3 in [0,R3)).  P2 = R3 (dense), P1 = 16*R3 + 1 (odd): in every pass the lanes of a warp
+// either walk d1 (odd stride) or consecutive slots, so the 128-bit accesses are bank-conflict free.
 template <int KT>
 struct PairGeo {
 	static constexpr int K = KT;
 	static constexpr int R3 = KT / 256; // 12 or 10
-	static constexpr int M1 = 16 * R3;  // items of passes 1 and 2
-	static constexpr int P2 = R3 + 1;
-	static constexpr int P1 = 16 * P2 + 1;
+	static constexpr int M1 = 16 * R3;  // items of the radix-16 passes
+	static constexpr int P2 = R3;
+	static constexpr int P1 = M1 + 1;
 	static constexpr int LEN = 16 * P1; // float4 slots
 	static_assert(KT == 3072 || KT == 2560, "paired FFT is specialised for the preset sizes");
-	// slot of input element n (natural order)
-	static __device__ __forceinline__ int slot_in(int n) {
-		const int n1 = n / M1, r = n - n1 * M1, n2 = r / R3, n3 = r - n2 * R3;
-		return n1 * P1 + n2 * P2 + n3;
-	}
-	// slot of output element k (digit-reversed placement)
-	static __device__ __forceinline__ int slot_out(int k) { return (k & 15) * P1 + ((k >> 4) & 15) * P2 + (k >> 8); }
+	// "slow-digit-first" index  i = d1*M1 + d2*R3 + d3  ->  slot (natural order up to the padding)
+	static __device__ __forceinline__ int slot_nat(int i) { return i + i / M1; }
+	// "fast-digit-first" index  i = d1 + 16*d2 + 256*d3  ->  slot (digit-reversed placement)
+	static __device__ __forceinline__ int slot_rev(int i) { return (i & 15) * P1 + ((i >> 4) & 15) * P2 + (i >> 8); }
 };
 
 __device__ __forceinline__ c2 ld_c2(const float4 *p) {
@@ -230,22 +232,18 @@ __device__ __forceinline__ void st_c2(float4 *p, c2 v) {
 	*p = make_float4(f2_lo(v.re), f2_hi(v.re), f2_lo(v.im), f2_hi(v.im));
 }
 
-// per-thread twiddle bases, loaded once per CTA: pass 1 item n' = n2*R3 + n3 needs W_K^(n'*q),
-// pass 2 item (k1, n3) needs W_M1^(n3*q) = W_K^(16*n3*q); q = 1,2,4,8 are loaded, the rest are products
+// per-thread twiddle bases, loaded once per CTA: w^(2^i), i = 0..3, of the thread's two radix-16 passes
+// (w = W_K^ia for the first, W_K^ib for the second); the other powers are products of at most three of them
 struct PairTw {
 	float2 a[4], b[4];
 };
 template <int KT>
-__device__ __forceinline__ PairTw pair_tw_load(const float2 *__restrict__ tw, int tid) {
-	using G = PairGeo<KT>;
+__device__ __forceinline__ PairTw pair_tw_load(const float2 *__restrict__ tw, int ia, int ib) {
 	PairTw t;
-	const int tt = tid < G::M1 ? tid : 0;
-	const int n2 = tt & 15, n3 = tt >> 4;
-	const int np = n2 * G::R3 + n3;
 #pragma unroll
 	for (int i = 0; i < 4; ++i) {
-		t.a[i] = __ldg(tw + ((np << i) % KT));
-		t.b[i] = __ldg(tw + ((16 * n3) << i) % KT);
+		t.a[i] = __ldg(tw + ((ia << i) % KT));
+		t.b[i] = __ldg(tw + ((ib << i) % KT));
 	}
 	return t;
 }
@@ -269,38 +267,81 @@ __device__ __forceinline__ void apply_tw16(c2 (&v)[16], const float2 (&base)[4])
 	});
 }
 
-// The three in-place passes over `buf` (PairGeo<KT>::LEN float4).  Contains __syncthreads(); every
-// thread of the 256-thread block must call it, the buffer must be complete and visible on entry,
-// and it is complete and visible on return (digit-reversed, see slot_out).
-template <bool INV, int KT>
-__device__ __forceinline__ void pair_fft(float4 *buf, const PairTw &tw, int tid) {
+// =====================  FORWARD transform, decimation in TIME (analysis)  =====================
+// Input x[n], n = n1 + 16*n2 + 256*n3, is placed at slot_rev(n); the result X[k], k = j3 + R3*j2 + M1*k1,
+// ends at slot_nat(k) -- and the last pass hands it to the caller in registers instead of storing it.
+//   stage A (caller): radix R3 over n3 for the thread's (n1, n2) = (tid & 15, tid >> 4): 12 contiguous slots,
+//                     no twiddle; fused with the windowing / pre-twiddle of the input (k_analyse2)
+//   stage B: item (n1, j3) = (tid & 15, tid >> 4), inputs n2 = 0..15 (stride P2) times W_M1^(n2*j3), radix 16 -> j2
+//   stage C: item m = j3 + R3*j2 = tid, inputs n1 = 0..15 (stride P1) times W_K^(n1*m), radix 16 -> k1;
+//            output q of the item is X[m + M1*q]
+template <int KT>
+__device__ __forceinline__ PairTw pair_tw_dit(const float2 *__restrict__ tw, int tid) {
 	using G = PairGeo<KT>;
-	if (tid < G::M1) { // pass 1: radix 16 over n1, item n' = (n2, n3), lanes walk n2 (stride P2)
-		const int n2 = tid & 15, n3 = tid >> 4;
-		float4 *p = buf + n2 * G::P2 + n3;
-		c2 v[16];
-		static_for<16>([&](auto qc) { v[decltype(qc)::value] = ld_c2(p + decltype(qc)::value * G::P1); });
-		PairDFT<16, INV>::run(v);
-		apply_tw16<INV>(v, tw.a);
-		static_for<16>([&](auto qc) { st_c2(p + decltype(qc)::value * G::P1, v[decltype(qc)::value]); });
-	}
-	__syncthreads();
-	if (tid < G::M1) { // pass 2: radix 16 over n2 inside block k1, item (k1, n3), lanes walk k1 (stride P1)
-		const int k1 = tid & 15, n3 = tid >> 4;
-		float4 *p = buf + k1 * G::P1 + n3;
+	const int t = tid < G::M1 ? tid : 0;
+	return pair_tw_load<KT>(tw, 16 * (t >> 4), t); // stage B: W_M1^j3 = W_K^(16*j3); stage C: W_K^m
+}
+template <int KT>
+__device__ __forceinline__ void pair_dit_stage_b(float4 *buf, const PairTw &tw, int tid) {
+	using G = PairGeo<KT>;
+	if (tid < G::M1) {
+		float4 *p = buf + (tid & 15) * G::P1 + (tid >> 4);
 		c2 v[16];
 		static_for<16>([&](auto qc) { v[decltype(qc)::value] = ld_c2(p + decltype(qc)::value * G::P2); });
-		PairDFT<16, INV>::run(v);
-		apply_tw16<INV>(v, tw.b);
+		apply_tw16<false>(v, tw.a);
+		PairDFT<16, false>::run(v);
+		static_for<16>([&](auto qc) { st_c2(p + decltype(qc)::value * G::P2, v[decltype(qc)::value]); });
+	}
+}
+// stage C for thread tid < M1: v[q] = X[tid + M1*q] on return (nothing is stored)
+template <int KT>
+__device__ __forceinline__ void pair_dit_stage_c(const float4 *buf, const PairTw &tw, int tid, c2 (&v)[16]) {
+	using G = PairGeo<KT>;
+	const float4 *p = buf + tid; // slot of (n1 = 0, j2, j3) is j2*P2 + j3 = m
+	static_for<16>([&](auto qc) { v[decltype(qc)::value] = ld_c2(p + decltype(qc)::value * G::P1); });
+	apply_tw16<false>(v, tw.b);
+	PairDFT<16, false>::run(v);
+}
+
+// =====================  INVERSE transform, decimation in FREQUENCY (synthesis)  =====================
+// Input Z[k], k = k1*M1 + k', enters pass 1 from registers (the caller loads it straight from HBM);
+// the result z[n], n = n1 + 16*n2 + 256*n3, ends at slot_rev(n).
+//   pass 1: item k' = tid (< M1), radix 16 over k1, times conj W_K^(k'*q), stored at slots q*P1 + k'
+//   pass 2: item (q1, r) = (tid & 15, tid >> 4) (< M1): radix 16 over the R3-strided digit, times conj W_M1^(r*q)
+//   pass 3: item (q1, q2) = (tid & 15, tid >> 4): radix R3 over the contiguous digit, no twiddle
+template <int KT>
+__device__ __forceinline__ PairTw pair_tw_dif(const float2 *__restrict__ tw, int tid) {
+	using G = PairGeo<KT>;
+	const int t = tid < G::M1 ? tid : 0;
+	return pair_tw_load<KT>(tw, t, 16 * (t >> 4));
+}
+// pass 1 for thread tid < M1: v[q] = Z[q*M1 + tid] on entry
+template <int KT>
+__device__ __forceinline__ void pair_dif_pass1(float4 *buf, const PairTw &tw, int tid, c2 (&v)[16]) {
+	using G = PairGeo<KT>;
+	PairDFT<16, true>::run(v);
+	apply_tw16<true>(v, tw.a);
+	float4 *p = buf + tid;
+	static_for<16>([&](auto qc) { st_c2(p + decltype(qc)::value * G::P1, v[decltype(qc)::value]); });
+}
+// passes 2 and 3 (contain the barriers between them and after); the buffer must be complete on entry
+template <int KT>
+__device__ __forceinline__ void pair_dif_pass23(float4 *buf, const PairTw &tw, int tid) {
+	using G = PairGeo<KT>;
+	if (tid < G::M1) {
+		float4 *p = buf + (tid & 15) * G::P1 + (tid >> 4);
+		c2 v[16];
+		static_for<16>([&](auto qc) { v[decltype(qc)::value] = ld_c2(p + decltype(qc)::value * G::P2); });
+		PairDFT<16, true>::run(v);
+		apply_tw16<true>(v, tw.b);
 		static_for<16>([&](auto qc) { st_c2(p + decltype(qc)::value * G::P2, v[decltype(qc)::value]); });
 	}
 	__syncthreads();
-	{ // pass 3: radix R3 over the contiguous n3, item (k1, k2), lanes walk k2 (stride P2)
-		const int k2 = tid & 15, k1 = tid >> 4;
-		float4 *p = buf + k1 * G::P1 + k2 * G::P2;
+	{
+		float4 *p = buf + (tid & 15) * G::P1 + (tid >> 4) * G::P2;
 		c2 v[G::R3];
 		static_for<G::R3>([&](auto qc) { v[decltype(qc)::value] = ld_c2(p + decltype(qc)::value); });
-		PairDFT<G::R3, INV>::run(v);
+		PairDFT<G::R3, true>::run(v);
 		static_for<G::R3>([&](auto qc) { st_c2(p + decltype(qc)::value, v[decltype(qc)::value]); });
 	}
 	__syncthreads();

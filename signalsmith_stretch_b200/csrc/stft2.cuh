@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 	float4 *buf = (float4 *)dyn_smem;
 	const int B = g.B, o = g.o, tid = threadIdx.x;
 	float *stA = (float *)(buf + G::LEN), *stB = stA + stage_len(B);
-	const PairTw tw = pair_tw_load<KT>(x.twiddle, tid);
+	const PairTw tw = pair_tw_dit<KT>(x.twiddle, tid);
 	const float2 pre0 = __ldg(x.pretw + tid); // exp(-i*pi*tid/N); element tid + 256*it gets a compile-time factor on top
 	const int PJ = g.C * x.maxFrames;         // pair slots per stream (2*C*maxFrames jobs)
 	const long long total = (long long)x.sCount * PJ;
@@ -122,8 +122,10 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 			continue;
 		}
 #endif
-		{ // ---- load stage: window, wrap-sign fold, half-bin pre-twiddle
+		{ // ---- load stage fused with the first FFT pass: window, wrap-sign fold, half-bin
+		  //      pre-twiddle of the thread's R3 samples n = tid + 256*n3, radix-R3 butterfly over n3 in registers
 			const int shA = x.inAligned ? (cur.a.start & 3) : 0, shB = x.inAligned ? (cur.b.start & 3) : 0;
+			c2 v[G::R3];
 			static_for<G::R3>([&](auto itc) {
 				constexpr int it = decltype(itc)::value;
 				const int n = tid + 256 * it, i0 = n + o, i1 = n + o - KT;
@@ -135,8 +137,11 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 				constexpr float fc = float(ct::cosq(256 * it, 4 * KT)), fs = -float(ct::sinq(256 * it, 4 * KT));
 				const float2 pw = cmulf(pre0, make_float2(fc, fs));
 				const c2 t = c2{muls(f2_make(a0, b0), w0), muls(f2_make(a1, b1), w1)}; // (x0*w0) + i*(x1*w1)
-				st_c2(buf + G::slot_in(n), cmulw(t, pw.x, pw.y));
+				v[it] = cmulw(t, pw.x, pw.y);
 			});
+			PairDFT<G::R3, false>::run(v);
+			float4 *p = buf + (tid & 15) * G::P1 + (tid >> 4) * G::P2;
+			static_for<G::R3>([&](auto qc) { st_c2(p + decltype(qc)::value, v[decltype(qc)::value]); });
 		}
 		__syncthreads(); // staging consumed, buf complete
 		const long long nitem = next_valid(item + gridDim.x, nxt);
@@ -144,21 +149,26 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 			stage_job(stA, nxt.s, nxt.a);
 			stage_job(stB, nxt.s, nxt.b);
 		}
-		pair_fft<false, KT>(buf, tw, tid);
-		{ // ---- unpack: bin b = Z[b/2] (b even) or conj(Z[K-1-b/2]) (b odd), Z digit-reversed in buf
+		pair_dit_stage_b<KT>(buf, tw, tid);
+		__syncthreads();
+		if (tid < G::M1) { // ---- last pass fused with the store: thread holds X[tid + M1*q], q = 0..15.
+			// bin b = Z[b/2] (b even) or conj(Z[K-1-b/2]) (b odd): Z[k] with k < K/2 (q < 8) is bin 2k, the rest bin 2(K-1-k)+1
+			c2 v[16];
+			pair_dit_stage_c<KT>(buf, tw, tid, v);
 			const bool hasB = cur.hasB, il = x.specIl;
 			// stereo direct path: the pair is (channel 0, channel 1) of one analysis and is stored interleaved
 			float4 *dst4 = (float4 *)x.spec + ((size_t)cur.s * 2 * x.maxFrames + (cur.a.row >> 1)) * g.K;
-			static_for<G::R3>([&](auto itc) {
-				const int b = tid + 256 * decltype(itc)::value;
-				const int hb = b >> 1, k = (b & 1) ? KT - 1 - hb : hb;
-				const float4 z = buf[G::slot_out(k)];
-				const float sg = (b & 1) ? -1.f : 1.f;
+			static_for<16>([&](auto qc) {
+				constexpr int q = decltype(qc)::value;
+				const int k = tid + G::M1 * q;
+				const int b = q < 8 ? 2 * k : 2 * (KT - 1 - k) + 1;
+				const float sg = q < 8 ? 1.f : -1.f;
+				const float ra = f2_lo(v[q].re), rb = f2_hi(v[q].re), ia = sg * f2_lo(v[q].im), ib = sg * f2_hi(v[q].im);
 				if (il) {
-					dst4[b] = make_float4(z.x, z.y, sg * z.z, sg * z.w);
+					dst4[b] = make_float4(ra, rb, ia, ib);
 				} else {
-					dstA[b] = make_float2(z.x, sg * z.z);
-					if (hasB) dstB[b] = make_float2(z.y, sg * z.w);
+					dstA[b] = make_float2(ra, ia);
+					if (hasB) dstB[b] = make_float2(rb, ib);
 				}
 			});
 		}
@@ -194,7 +204,7 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 		pend[i] = gp[i];
 		wp[i] = gw[i];
 	}
-	const PairTw tw = pair_tw_load<KT>(x.twiddle, tid);
+	const PairTw tw = pair_tw_dif<KT>(x.twiddle, tid);
 	const Frame *frames = x.frames + (size_t)s * x.maxFrames;
 	__syncthreads();
 	int head = 0, emitted = 0;
@@ -221,13 +231,19 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 		const int gap = hasB ? frames[f + 1].t - tA : 0;
 		const float2 *YA = x.Y + coef_off(x, s, f, c), *YB = x.Y + coef_off(x, s, hasB ? f + 1 : f, c);
 #ifndef B200S_EMU_EXACT_FFT
-		// ---- output spectra of the two blocks -> registers (in flight while the ring is being emitted)
-		float2 ya[G::R3], yb[G::R3];
-		static_for<G::R3>([&](auto itc) {
-			constexpr int it = decltype(itc)::value;
-			ya[it] = YA[tid + 256 * it];
-			yb[it] = YB[tid + 256 * it];
-		});
+		// ---- first inverse-FFT pass takes its inputs straight from HBM (in flight while the ring is being emitted):
+		//      Z'[k] = Y[2k] for k < K/2, conj(Y[2(K-1-k)+1]) otherwise; thread tid < M1 needs k = q*M1 + tid, q = 0..15
+		c2 v[16];
+		if (tid < G::M1) {
+			static_for<16>([&](auto qc) {
+				constexpr int q = decltype(qc)::value;
+				const int k = q * G::M1 + tid;
+				const int b = q < 8 ? 2 * k : 2 * (KT - 1 - k) + 1;
+				const float sg = q < 8 ? 1.f : -1.f;
+				const float2 a = YA[b], bb = YB[b];
+				v[q] = c2{f2_make(a.x, bb.x), f2_make(sg * a.y, sg * bb.y)};
+			});
+		}
 #endif
 		emit(tA - emitted);
 #ifdef B200S_EMU_EXACT_FFT // test builds only
@@ -239,15 +255,9 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 		}
 		__syncthreads();
 #else
-		// ---- Z'[k]: k = b/2 takes Y[b] (b even), k = K-1-b/2 takes conj(Y[b]) (b odd); natural-order slots
-		static_for<G::R3>([&](auto itc) {
-			constexpr int it = decltype(itc)::value;
-			const int b = tid + 256 * it, hb = b >> 1, k = (b & 1) ? KT - 1 - hb : hb;
-			const float sg = (b & 1) ? -1.f : 1.f;
-			buf[G::slot_in(k)] = make_float4(ya[it].x, yb[it].x, sg * ya[it].y, sg * yb[it].y);
-		});
+		if (tid < G::M1) pair_dif_pass1<KT>(buf, tw, tid, v);
 		__syncthreads(); // buf complete; the emission above is complete too
-		pair_fft<true, KT>(buf, tw, tid);
+		pair_dif_pass23<KT>(buf, tw, tid);
 #endif
 		// ---- one sweep over the ring: slot j ahead of the head gets, in the reference's order,
 		//      block A's sample j-addOff, the emission if j < gap, then block B's sample (relative to the new head)
@@ -259,7 +269,7 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 #else
 			const bool hi = i >= o;
 			const int n2 = hi ? i - o : i - o + KT;
-			const float4 z = buf[G::slot_out(n2)];
+			const float4 z = buf[G::slot_rev(n2)];
 			const float2 p = __ldg(x.pretw + n2);
 			const float re = second ? z.y : z.x, im = second ? z.w : z.z;
 			const float y = hi ? (re * p.x + im * p.y) : (im * p.x - re * p.y);
