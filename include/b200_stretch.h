@@ -50,6 +50,10 @@ int b200s_synchronize(b200s_engine *e);
 /* process() can split the batch into up to 4 sub-batches on prioritised CUDA streams so that the
  * different kernels of its launch sequence overlap (default 1 = off). */
 int b200s_set_sub_batches(b200s_engine *e, int n);
+/* Implementation selectors for A/B measurement and cross-checking (results are identical by contract):
+ *   key 0: direct chain kernel generation (1, 2, 3; 0 = default)   key 1: FFT kernels (1 = scalar Stockham, 0 = default paired)
+ *   key 2: stream groups of the host-buffer pipeline in b200s_process (1..8) */
+int b200s_set_tuning(b200s_engine *e, int key, int value);
 
 /* ---- configuration: presetDefault / presetCheaper / configure / reset  (:49-94) ---- */
 int b200s_preset_default(b200s_engine *e, int channels, float sample_rate, int split_computation);

@@ -21,7 +21,7 @@ _LIB_NAME = "libb200stretch.so"
 
 # every symbol include/b200_stretch.h declares
 ABI_SYMBOLS = [
-    "b200s_create", "b200s_destroy", "b200s_last_error", "b200s_version", "b200s_set_stream", "b200s_synchronize", "b200s_set_sub_batches",
+    "b200s_create", "b200s_destroy", "b200s_last_error", "b200s_version", "b200s_set_stream", "b200s_synchronize", "b200s_set_sub_batches", "b200s_set_tuning",
     "b200s_preset_default", "b200s_preset_cheaper", "b200s_configure", "b200s_reset", "b200s_reserve",
     "b200s_batch", "b200s_channels", "b200s_block_samples", "b200s_interval_samples", "b200s_input_latency",
     "b200s_output_latency", "b200s_split_computation", "b200s_seek_length", "b200s_output_seek_length",
@@ -74,7 +74,7 @@ def _bind(lib):
     sig = {
         "b200s_create": (ci, [ci, cl, ci, ctypes.POINTER(vp)]), "b200s_destroy": (None, [vp]),
         "b200s_last_error": (ctypes.c_char_p, [vp]), "b200s_version": (ci, [ip, ip, ip]),
-        "b200s_set_stream": (ci, [vp, vp]), "b200s_synchronize": (ci, [vp]), "b200s_set_sub_batches": (ci, [vp, ci]),
+        "b200s_set_stream": (ci, [vp, vp]), "b200s_synchronize": (ci, [vp]), "b200s_set_sub_batches": (ci, [vp, ci]), "b200s_set_tuning": (ci, [vp, ci, ci]),
         "b200s_preset_default": (ci, [vp, ci, cf, ci]), "b200s_preset_cheaper": (ci, [vp, ci, cf, ci]),
         "b200s_configure": (ci, [vp, ci, ci, ci, ci]), "b200s_reset": (ci, [vp]), "b200s_reserve": (ci, [vp, ci, ci]),
         "b200s_output_seek_length": (ci, [vp, cf]),
@@ -286,6 +286,10 @@ class BatchStretch:
     # ---- plumbing ----
     def set_stream(self, cuda_stream):
         self._ck(self._lib.b200s_set_stream(self._h, ctypes.c_void_p(int(cuda_stream))))
+
+    def set_tuning(self, key, value):
+        """Implementation selectors (include/b200_stretch.h): 0 chain kernel generation, 1 scalar FFT kernels, 2 host pipeline groups."""
+        self._ck(self._lib.b200s_set_tuning(self._h, int(key), int(value)))
 
     def set_sub_batches(self, n):
         self._ck(self._lib.b200s_set_sub_batches(self._h, n))

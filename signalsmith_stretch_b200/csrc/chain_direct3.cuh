@@ -73,28 +73,41 @@ __device__ __forceinline__ f2 fsqrtq2(f2 a) { // fsqrtq (kernels.cuh) on both el
 #endif
 __device__ __forceinline__ f2 sel_f2(bool p, f2 a) { return f2_make(p ? f2_lo(a) : 0.f, p ? f2_hi(a) : 0.f); }
 __device__ __forceinline__ c2 sel_c2(bool p, c2 a) { return c2{sel_f2(p, a.re), sel_f2(p, a.im)}; }
+
+// EXACT sum / difference of two packed values of which at least one is a product.  ptxas (12.9) contracts
+// mul.rn.f32x2 followed by add/sub.rn.f32x2 into FMUL2 + FFMA2 even with --fmad=false (measured; the scalar
+// .rn forms are never contracted), which would round differently from the reference's separate multiply and
+// add.  p*one + q with `one` = 1.0f from a kernel parameter (opaque to the compiler) is the same correctly
+// rounded p + q in one FFMA2 and cannot absorb the multiply that produced p.
+#ifdef B200S_EMU
+__device__ __forceinline__ f2 padd(f2 p, f2 q, float) { return p + q; }
+__device__ __forceinline__ f2 psub(f2 p, f2 q, float) { return p - q; }
+#else
+__device__ __forceinline__ f2 padd(f2 p, f2 q, float one) { return fma2(p, f2_make(one, one), q); }
+__device__ __forceinline__ f2 psub(f2 p, f2 q, float one) { return fma2(p, f2_make(one, one), neg2(q)); }
+#endif
 // xmul: a * b, both packed
-__device__ __forceinline__ c2 xmul2(c2 a, c2 b) {
-	return c2{mul2(a.re, b.re) - mul2(a.im, b.im), mul2(a.re, b.im) + mul2(a.im, b.re)};
+__device__ __forceinline__ c2 xmul2(c2 a, c2 b, float one) {
+	return c2{psub(mul2(a.re, b.re), mul2(a.im, b.im), one), padd(mul2(a.re, b.im), mul2(a.im, b.re), one)};
 }
 // xmul with a scalar complex factor on the right (rotation): a * r
-__device__ __forceinline__ c2 xmul2s(c2 a, float2 r) {
-	return c2{muls(a.re, r.x) - muls(a.im, r.y), muls(a.re, r.y) + muls(a.im, r.x)};
+__device__ __forceinline__ c2 xmul2s(c2 a, float2 r, float one) {
+	return c2{psub(muls(a.re, r.x), muls(a.im, r.y), one), padd(muls(a.re, r.y), muls(a.im, r.x), one)};
 }
 // xmulc: a * conj(b) in the scalar helper's operand order (b.x*a.x + b.y*a.y, b.x*a.y - b.y*a.x)
-__device__ __forceinline__ c2 xmulc2(c2 a, c2 b) {
-	return c2{mul2(b.re, a.re) + mul2(b.im, a.im), mul2(b.re, a.im) - mul2(b.im, a.re)};
+__device__ __forceinline__ c2 xmulc2(c2 a, c2 b, float one) {
+	return c2{padd(mul2(b.re, a.re), mul2(b.im, a.im), one), psub(mul2(b.re, a.im), mul2(b.im, a.re), one)};
 }
-__device__ __forceinline__ f2 xnorm2(c2 a) { return mul2(a.re, a.re) + mul2(a.im, a.im); }
+__device__ __forceinline__ f2 xnorm2(c2 a, float one) { return padd(mul2(a.re, a.re), mul2(a.im, a.im), one); }
 // low + (high - low)*frac, frac common to both channels
-__device__ __forceinline__ c2 xlerp2p(c2 lo, c2 hi, float fr) {
-	return c2{lo.re + muls(hi.re - lo.re, fr), lo.im + muls(hi.im - lo.im, fr)};
+__device__ __forceinline__ c2 xlerp2p(c2 lo, c2 hi, float fr, float one) {
+	return c2{padd(muls(hi.re - lo.re, fr), lo.re, one), padd(muls(hi.im - lo.im, fr), lo.im, one)};
 }
 // Prediction::makeOutput (:596-603) for both channels
-__device__ __forceinline__ c2 make_output_q2(c2 phase, f2 energy, c2 input) {
-	const f2 pn = xnorm2(phase);
+__device__ __forceinline__ c2 make_output_q2(c2 phase, f2 energy, c2 input, float one) {
+	const f2 pn = xnorm2(phase, one);
 	const bool w0 = f2_lo(pn) <= B200S_NOISE_FLOOR, w1 = f2_hi(pn) <= B200S_NOISE_FLOOR;
-	const f2 pni = xnorm2(input) + f2_make(B200S_NOISE_FLOOR, B200S_NOISE_FLOOR);
+	const f2 pni = xnorm2(input, one) + f2_make(B200S_NOISE_FLOOR, B200S_NOISE_FLOOR);
 	const c2 ph = c2{f2_make(w0 ? f2_lo(input.re) : f2_lo(phase.re), w1 ? f2_hi(input.re) : f2_hi(phase.re)),
 	                 f2_make(w0 ? f2_lo(input.im) : f2_lo(phase.im), w1 ? f2_hi(input.im) : f2_hi(phase.im))};
 	const f2 pn2 = f2_make(w0 ? f2_lo(pni) : f2_lo(pn), w1 ? f2_hi(pni) : f2_hi(pn));
@@ -123,6 +136,7 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 	// chunk fill: lane -> (bin offset, row within a group of 4); a quarter-warp covers 4 bins (64 B) of 2 rows
 	const int fillI = (lane & 3) | (((lane >> 3) & 1) << 2), fillF = ((lane >> 2) & 1) | (((lane >> 4) & 1) << 1);
 	const float2 rot0 = x.rot0, rotStep = x.rotStep;
+	const float one = x.one; // 1.0f, opaque to the compiler (see padd / psub)
 
 	for (int base = 0; base < cl.nFrames; base += 32) {
 		__syncwarp();
@@ -163,6 +177,14 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 		float2 rotq = rotOn ? rot0 : make_float2(1.f, 0.f); // rot[q] by the reference's float recurrence (:647-655)
 		const float2 rotS = rotOn ? rotStep : make_float2(1.f, 0.f);
 		const int steps = K + LT + D * (nAct - 1);
+		// first chunk start from which every ACTIVE lane has q - L*tf - 1 >= 0 and b = q - L >= L (inactive lanes only
+		// produce values nobody consumes): q >= D*(nAct-1) + 2L + ceil(max L*tf) + 1
+		int interiorFrom;
+		{
+			float mx = active ? longTf : 0.f;
+			for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+			interiorFrom = D * (nAct - 1) + 2 * LT + (int)ceilf(mx) + 2;
+		}
 		for (int k0 = 0; k0 < steps; k0 += CHAIN_CH) {
 			// ---------------- stage the chunk: 8 new bins per block, both channels per 16-byte copy ----------------
 #pragma unroll
@@ -184,12 +206,14 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 			cp_async_wait_all();
 			__syncwarp();
 			// ---------------- CHAIN_CH steps ----------------
-			auto step = [&](const int i, auto farTag) {
-				constexpr bool FAR = decltype(farTag)::value;
+			// INTERIOR: every lane's q, b and interpolation points are inside [0, K) for the whole chunk, so all the
+			// edge masks below are identities and are compiled out (about nine chunks in ten)
+			auto step = [&](const int i, auto farTag, auto intTag) {
+				constexpr bool FAR = decltype(farTag)::value, INTERIOR = decltype(intTag)::value;
 				const int q = k0 + i - D * lane;
 				const int b = q - LT;
-				const bool qIn = active && (unsigned)q < (unsigned)K;
-				const bool bIn = active && (unsigned)b < (unsigned)K;
+				const bool qIn = INTERIOR || (active && (unsigned)q < (unsigned)K);
+				const bool bIn = INTERIOR ? active : (active && (unsigned)b < (unsigned)K);
 				// the twists need input interpolated at q - L*tf and (b+1) - tf  (:750,:757)
 				const float i2 = fsub((float)q, longTf);
 				const int l2 = (int)floorf(i2);
@@ -214,30 +238,30 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 				c2 pv = ld_c2s(&U.pvy[i][lane]);
 				c2 lo2, hi2, lo1, hi1;
 				if constexpr (!FAR) {
-					lo2 = sel_c2(l2 >= 0, ld_c2s(&U.in[l2 & (CH3_RING - 1)][lane]));
-					hi2 = sel_c2(l2 >= -1, ld_c2s(&U.in[(l2 + 1) & (CH3_RING - 1)][lane]));
-					lo1 = sel_c2(l1 >= 0, ld_c2s(&U.in[l1 & (CH3_RING - 1)][lane]));
-					hi1 = sel_c2(l1 >= -1, ld_c2s(&U.in[(l1 + 1) & (CH3_RING - 1)][lane]));
+					lo2 = sel_c2(INTERIOR || l2 >= 0, ld_c2s(&U.in[l2 & (CH3_RING - 1)][lane]));
+					hi2 = sel_c2(INTERIOR || l2 >= -1, ld_c2s(&U.in[(l2 + 1) & (CH3_RING - 1)][lane]));
+					lo1 = sel_c2(INTERIOR || l1 >= 0, ld_c2s(&U.in[l1 & (CH3_RING - 1)][lane]));
+					hi1 = sel_c2(INTERIOR || l1 >= -1, ld_c2s(&U.in[(l1 + 1) & (CH3_RING - 1)][lane]));
 				} else { // extreme stretch (> 2x): gather straight from the spectrum row
 					lo2 = (l2 < 0 || l2 >= K) ? zc : ld_c2s(myIn + l2);
 					hi2 = (l2 + 1 < 0 || l2 + 1 >= K) ? zc : ld_c2s(myIn + l2 + 1);
 					lo1 = (l1 < 0 || l1 >= K) ? zc : ld_c2s(myIn + l1);
 					hi1 = (l1 + 1 < 0 || l1 + 1 >= K) ? zc : ld_c2s(myIn + l1 + 1);
 				}
-				pv = xmul2s(pv, rotq); // :653-654 rotate Band::output and Band::prevInput by one interval
-				ro = xmul2s(ro, rotq);
-				const f2 e = xnorm2(inq);                       // :679 (identity map: energy = |input|^2)
-				const c2 ph0 = xmul2(ro, xmulc2(inq, pv));      // :714-715
+				pv = xmul2s(pv, rotq, one); // :653-654 rotate Band::output and Band::prevInput by one interval
+				ro = xmul2s(ro, rotq, one);
+				const f2 e = xnorm2(inq, one);                       // :679 (identity map: energy = |input|^2)
+				const c2 ph0 = xmul2(ro, xmulc2(inq, pv, one), one);      // :714-715
 				const f2 den = f2_make(fmaxf(f2_lo(re), f2_lo(e)), fmaxf(f2_hi(re), f2_hi(e))) + f2_make(B200S_NOISE_FLOOR, B200S_NOISE_FLOOR);
 				const c2 newPre = sel_c2(qIn, c2{fdivq2(ph0.re, den), fdivq2(ph0.im, den)}); // :716
 				const f2 newE = sel_f2(qIn, e);
 				const c2 newIn = sel_c2(qIn, inq);
-				const c2 newT2 = sel_c2(qIn, xmulc2(inq, xlerp2p(lo2, hi2, f2s))); // long twist at q (:758)
+				const c2 newT2 = sel_c2(qIn, xmulc2(inq, xlerp2p(lo2, hi2, f2s, one), one)); // long twist at q (:758)
 				// short twist at b+1 (:751,:771): Prediction::input[b+1] is inF[1] before the shift
-				const c2 t1N = xmulc2(LT > 1 ? inF[LT > 1 ? 1 : 0] : newIn, xlerp2p(lo1, hi1, f1s));
+				const c2 t1N = xmulc2(LT > 1 ? inF[LT > 1 ? 1 : 0] : newIn, xlerp2p(lo1, hi1, f1s, one), one);
 				{
 					const float2 rn = xmul(rotq, rotS);
-					rotq = make_float2(q >= 0 ? rn.x : rotq.x, q >= 0 ? rn.y : rotq.y);
+					rotq = make_float2((INTERIOR || q >= 0) ? rn.x : rotq.x, (INTERIOR || q >= 0) ? rn.y : rotq.y);
 				}
 				// ---- FIFO rotation (pure renaming after unrolling): what falls out belongs to bin b
 				const f2 eB = eF[0];
@@ -256,19 +280,20 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 				// ---- main prediction at bin b (:727-800): the louder channel (first on ties, :733) leads
 				const bool m = f2_hi(eB) > f2_lo(eB);
 				const float maxE = m ? f2_hi(eB) : f2_lo(eB);
-				const float2 oh1 = pick(m, oh[0]), ohL = pick(m, oh[LT - 1]), pr1 = pick(m, pre[0]), prL = pick(m, pre[LT - 1]);
-				const float2 t1b = pick(m, t1P), t2b = pick(m, t2B), t1n = pick(m, t1N), t2n = pick(m, t2F[LT - 1]), pinM = pick(m, inB);
-				float2 phase = make_float2(0.f, 0.f);
-				phase = xadd(phase, sel2(b > 0, xmul(oh1, t1b)));         // :754
-				phase = xadd(phase, sel2(b >= LT, xmul(ohL, t2b)));       // :761
-				phase = xadd(phase, sel2(b < K - 1, xmulc(pr1, t1n)));    // :774
-				phase = xadd(phase, sel2(b < K - LT, xmulc(prL, t2n)));   // :784
+				// the phase sum of :754-784 is formed for both channels at once (packed, each channel from its own
+				// registers, exactly as if it were the leader) and the leader's is picked afterwards
+				c2 ph2 = zc;
+				ph2 = ph2 + sel_c2(INTERIOR || b > 0, xmul2(oh[0], t1P, one));                      // :754
+				ph2 = ph2 + sel_c2(INTERIOR || b >= LT, xmul2(oh[LT - 1], t2B, one));               // :761
+				ph2 = ph2 + sel_c2(INTERIOR || b < K - 1, xmulc2(pre[0], t1N, one));                // :774
+				ph2 = ph2 + sel_c2(INTERIOR || b < K - LT, xmulc2(pre[LT - 1], t2F[LT - 1], one)); // :784
+				const float2 phase = pick(m, ph2), pinM = pick(m, inB);
 				const float2 outM = make_output_q(phase, maxE, pinM);     // :788
 				// the other channel is locked in phase (:791-799); computed for both, the leader keeps outM
 				//   cph = xmul(outM, xmulc(inB_c, pinM)), operand order of the scalar helpers
-				const c2 tw = c2{muls(inB.re, pinM.x) + muls(inB.im, pinM.y), muls(inB.im, pinM.x) - muls(inB.re, pinM.y)};
-				const c2 cph = c2{muls(tw.re, outM.x) - muls(tw.im, outM.y), muls(tw.im, outM.x) + muls(tw.re, outM.y)};
-				const c2 other = make_output_q2(cph, eB, inB);
+				const c2 tw = c2{padd(muls(inB.re, pinM.x), muls(inB.im, pinM.y), one), psub(muls(inB.im, pinM.x), muls(inB.re, pinM.y), one)};
+				const c2 cph = c2{psub(muls(tw.re, outM.x), muls(tw.im, outM.y), one), padd(muls(tw.im, outM.x), muls(tw.re, outM.y), one)};
+				const c2 other = make_output_q2(cph, eB, inB, one);
 				const c2 oc = c2{f2_make(m ? f2_lo(other.re) : outM.x, m ? outM.x : f2_hi(other.re)),
 				                 f2_make(m ? f2_lo(other.im) : outM.y, m ? outM.y : f2_hi(other.im))};
 				// unconditional: out-of-range steps only produce values that every consumer masks
@@ -284,13 +309,18 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 				}
 				U.pvy[i][lane] = make_float4(f2_lo(oc.re), f2_hi(oc.re), f2_lo(oc.im), f2_hi(oc.im));
 			};
-			if (!farAny) { // fully unrolled, branch-free: one basic block the scheduler can interleave
-#pragma unroll
-				for (int i = 0; i < CHAIN_CH; ++i) step(i, std::false_type{});
-			} else {
+			// unrolled by 4 (for L = 4 the register FIFOs rotate by pure renaming) so that the hot loop stays in the
+			// instruction cache; branch-free inside
+			auto run_chunk = [&](auto farTag, auto intTag) {
 #pragma unroll 1
-				for (int i = 0; i < CHAIN_CH; ++i) step(i, std::true_type{});
-			}
+				for (int h = 0; h < CHAIN_CH; h += 4) {
+#pragma unroll
+					for (int u = 0; u < 4; ++u) step(h + u, farTag, intTag);
+				}
+			};
+			if (farAny) run_chunk(std::true_type{}, std::false_type{});
+			else if (k0 >= interiorFrom && k0 + CHAIN_CH <= K) run_chunk(std::false_type{}, std::true_type{});
+			else run_chunk(std::false_type{}, std::false_type{});
 			__syncwarp();
 			// ---------------- write the chunk's finals back: planar Band::output rows, 32 B per row and quarter-warp ----------------
 #pragma unroll

@@ -114,6 +114,7 @@ struct Ctx {
 	// stIl [S][2][K] holds such copies of stIn / stPrev, made by k_plan at the start of the call
 	float4 *stIl;
 	int specIl;
+	float one; // 1.0f; passed as data so that ptxas cannot fold the exact packed add p*one + q (chain_direct3.cuh)
 	// call scratch
 	int maxFrames;
 	Frame *frames; // [S][maxFrames]

@@ -39,7 +39,8 @@ struct b200s_engine {
 	int nSub = 1, maxSub = 1;
 	cudaStream_t subStream[kMaxSub] = {0, 0, 0, 0, 0, 0, 0, 0};
 	cudaEvent_t evBegin = 0, evSubDone[kMaxSub] = {0, 0, 0, 0, 0, 0, 0, 0};
-	int nHostParts = 4; // host-buffer API: stream groups whose H2D copy / kernels / D2H copy are pipelined
+	int chainV = 0, fftV1 = 0; // b200s_set_tuning overrides (0 = default)
+	int nHostParts = 8; // host-buffer API: stream groups whose H2D copy / kernels / D2H copy are pipelined
 	cudaEvent_t evStart = 0, evStop = 0;
 	long long launches = 0;
 	std::string err;
@@ -129,6 +130,7 @@ static Ctx make_ctx(b200s_engine *e) {
 	x.window = e->dWindow; x.winProd = e->dWinProd; x.wpReset = e->dWpReset;
 	x.rot = e->dRot; x.twiddle = e->dTwiddle; x.pretw = e->dPretw;
 	x.rot0 = e->rot0; x.rotStep = e->rotStep;
+	x.one = 1.0f;
 	x.sched = e->dSched;
 	x.histCur = e->dHist[e->histCur]; x.histNext = e->dHist[e->histCur ^ 1];
 	x.pend = e->dPend; x.pendWp = e->dPendWp;
@@ -186,10 +188,10 @@ static int prof_mark(b200s_engine *e, int kind, bool begin) {
 typedef void (*ChainKernel)(Ctx);
 static ChainKernel analyse_kernel(const Cfg &g) { return g.K == 3072 ? k_analyse<3072> : g.K == 2560 ? k_analyse<2560> : k_analyse<0>; }
 // paired in-place FFT kernels (stft2.cuh) for the preset sizes
-static bool use_pair_fft(const Cfg &g) {
+static bool use_pair_fft(const Cfg &g, int forceV1 = 0) {
 	static int v1 = -1;
 	if (v1 < 0) v1 = getenv("B200S_FFT_V1") ? 1 : 0; // A/B switch for profiling the first-generation kernels
-	return !v1 && (g.K == 3072 || g.K == 2560);
+	return !v1 && !forceV1 && (g.K == 3072 || g.K == 2560);
 }
 static ChainKernel analyse2_kernel(const Cfg &g) { return g.K == 3072 ? k_analyse2<3072> : k_analyse2<2560>; }
 static ChainKernel synth2_kernel(const Cfg &g) { return g.K == 3072 ? k_synth2<3072> : k_synth2<2560>; }
@@ -229,14 +231,14 @@ static int chain2_warps(const Cfg &g, int nOut) {
 }
 // which direct chain kernel: 3 = packed stereo (chain_direct3.cuh, needs the paired analysis kernel),
 // 2 = lane-per-(block,channel) multi-warp (chain_direct2.cuh), 1 = first generation; B200S_CHAIN_V overrides (A/B profiling)
-static int chain_version(const Cfg &g) {
+static int chain_version(const Cfg &g, int override, int forceFftV1) {
 	static int env = -1;
 	if (env < 0) {
 		const char *v = getenv("B200S_CHAIN_V");
 		env = v ? atoi(v) : 0;
 	}
-	int want = env ? env : 3;
-	if (want == 3 && !(g.C == 2 && use_pair_fft(g))) want = 2;
+	int want = override ? override : env ? env : 3;
+	if (want == 3 && !(g.C == 2 && use_pair_fft(g, forceFftV1))) want = 2;
 	return want;
 }
 static ChainKernel chain3_kernel(const Cfg &g) {
@@ -496,7 +498,8 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	const int nSub = (e->profiling || wantSub <= 1 || g.S < 64) ? 1 : std::min(wantSub, e->maxSub);
 	if (nSub > 1) CK(cudaEventRecord(e->evBegin, e->stream));
 	const bool plain = !(e->prm.mapN > 0 || e->prm.freqMultiplier != 1.0f) && e->prm.formantMultiplier == 1.0f;
-	const int chainV = chain_version(g);
+	const int chainV = chain_version(g, e->chainV, e->fftV1);
+	const bool pairFft = use_pair_fft(g, e->fftV1);
 	x.specIl = (plain && chainV == 3) ? 1 : 0;
 	for (int sub = 0; sub < nSub; ++sub) {
 		cudaStream_t st = nSub > 1 ? e->subStream[sub] : e->stream;
@@ -508,7 +511,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 		{ // (profiling implies nSub == 1, i.e. st == e->stream, which is where PROF() records its events)
 			PROF(PK_PLAN, B200S_LAUNCH(k_plan, dim3(x.sCount), dim3(kThreads), 0, st, x));
 			if (F > 0) {
-				if (use_pair_fft(g)) { // persistent CTAs, two per SM, over the (stream, job pair) items
+				if (pairFft) { // persistent CTAs, two per SM, over the (stream, job pair) items
 					const long long items = (long long)x.sCount * g.C * x.maxFrames;
 					const int grid = (int)std::min<long long>(items, 2LL * e->numSMs);
 					PROF(PK_ANALYSE, B200S_LAUNCH(analyse2_kernel(g), dim3(grid), dim3(256), smem_analyse2(g), st, x));
@@ -531,7 +534,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 					PROF(PK_CHAIN, B200S_LAUNCH(kc, grid, block, smem_chain(g, plain), st, x));
 				}
 			}
-			if (use_pair_fft(g)) {
+			if (pairFft) {
 				PROF(PK_SYNTH, B200S_LAUNCH(synth2_kernel(g), dim3(g.C, x.sCount), dim3(256), smem_synth2(g), st, x));
 			} else {
 				ChainKernel ks = synth_kernel(g);
@@ -705,6 +708,17 @@ int b200s_set_stream(b200s_engine *e, void *cuda_stream) {
 int b200s_set_sub_batches(b200s_engine *e, int n) {
 	if (!e || n < 1) return B200S_EINVAL;
 	e->nSub = n > e->maxSub ? e->maxSub : n;
+	return 0;
+}
+int b200s_set_tuning(b200s_engine *e, int key, int value) {
+	if (!e) return B200S_EINVAL;
+	if (key == 0 && value >= 0 && value <= 3) e->chainV = value;
+	else if (key == 1 && (value == 0 || value == 1)) e->fftV1 = value;
+	else if (key == 2 && value >= 1) e->nHostParts = std::min(value, (int)b200s_engine::kMaxSub);
+	else {
+		e->err = "b200s_set_tuning: unknown key or value";
+		return B200S_EINVAL;
+	}
 	return 0;
 }
 int b200s_synchronize(b200s_engine *e) {

@@ -220,3 +220,38 @@ def test_fast_div_sqrt_are_correctly_rounded(gpu):
     e = gpu(1)
     bad_div, bad_sqrt = e.selftest_divsqrt(1 << 27, 12345)
     assert bad_div == 0 and bad_sqrt == 0, (bad_div, bad_sqrt)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("blocks_per_call", [7, 40])
+def test_chain_kernel_generations_agree_bit_exactly(gpu, blocks_per_call):
+    """The three direct chain kernels (scalar lane-per-block, lane-per-(block,channel) multi-warp, packed f32x2
+    stereo) implement the same arithmetic: on identical spectra their outputs must be identical bit for bit
+    (guards the packed kernel against compiler contraction of multiply-add pairs).  40 blocks per call also
+    exercises the second group / the warp hand-off."""
+    cfg, C, sr, ratio, kind = signals.CONFIGS["config2_stereo_0p8x"]
+    outs = []
+    for gen in (1, 2, 3):
+        e = gpu(5)
+        cfg(e)
+        e.set_tuning(0, gen)
+        H = e.intervalSamples()
+        n_out = 3 * blocks_per_call * H
+        x = signals.batch(kind, 5, C, int(round(n_out / ratio)), sr)
+        outs.append(signals.run_batch(e, x, ratio, blocks_per_call * H))
+    assert np.array_equal(outs[0], outs[1]), "gen 2 differs: max %g" % np.abs(outs[0] - outs[1]).max()
+    assert np.array_equal(outs[0], outs[2]), "gen 3 differs: max %g" % np.abs(outs[0] - outs[2]).max()
+
+
+@pytest.mark.gpu
+def test_paired_fft_kernels_match_scalar_fft_kernels(gpu):
+    """Paired in-place packed FFT kernels vs the first-generation scalar Stockham kernels: same transform,
+    different rounding -- identity configuration agrees to float precision."""
+    outs = []
+    for v1 in (1, 0):
+        e = gpu(3)
+        e.presetDefault(2, 48000.0)
+        e.set_tuning(1, v1)
+        x = signals.batch("harmonic", 3, 2, 48000, 48000)
+        outs.append(signals.run_batch(e, x, 1.0, 7200))
+    assert rms(outs[0] - outs[1]) <= 2e-7
