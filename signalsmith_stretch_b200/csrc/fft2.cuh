@@ -324,9 +324,11 @@ __device__ __forceinline__ void pair_dif_pass1(float4 *buf, const PairTw &tw, in
 	float4 *p = buf + tid;
 	static_for<16>([&](auto qc) { st_c2(p + decltype(qc)::value * G::P1, v[decltype(qc)::value]); });
 }
-// passes 2 and 3 (contain the barriers between them and after); the buffer must be complete on entry
+// pass 2 (in place; the buffer must be complete on entry) and pass 3, which leaves its outputs in registers:
+// for thread (q1, q2) = (tid & 15, tid >> 4), v[q3] = z[q1 + 16*q2 + 256*q3] on return.  Contains the barrier
+// between the two passes; the caller decides where the results go.
 template <int KT>
-__device__ __forceinline__ void pair_dif_pass23(float4 *buf, const PairTw &tw, int tid) {
+__device__ __forceinline__ void pair_dif_pass23(float4 *buf, const PairTw &tw, int tid, c2 (&out)[PairGeo<KT>::R3]) {
 	using G = PairGeo<KT>;
 	if (tid < G::M1) {
 		float4 *p = buf + (tid & 15) * G::P1 + (tid >> 4);
@@ -338,13 +340,10 @@ __device__ __forceinline__ void pair_dif_pass23(float4 *buf, const PairTw &tw, i
 	}
 	__syncthreads();
 	{
-		float4 *p = buf + (tid & 15) * G::P1 + (tid >> 4) * G::P2;
-		c2 v[G::R3];
-		static_for<G::R3>([&](auto qc) { v[decltype(qc)::value] = ld_c2(p + decltype(qc)::value); });
-		PairDFT<G::R3, true>::run(v);
-		static_for<G::R3>([&](auto qc) { st_c2(p + decltype(qc)::value, v[decltype(qc)::value]); });
+		const float4 *p = buf + (tid & 15) * G::P1 + (tid >> 4) * G::P2;
+		static_for<G::R3>([&](auto qc) { out[decltype(qc)::value] = ld_c2(p + decltype(qc)::value); });
+		PairDFT<G::R3, true>::run(out);
 	}
-	__syncthreads();
 }
 
 } // namespace b200s

@@ -40,7 +40,6 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 	const int B = g.B, o = g.o, tid = threadIdx.x;
 	float *stA = (float *)(buf + G::LEN), *stB = stA + stage_len(B);
 	const PairTw tw = pair_tw_dit<KT>(x.twiddle, tid);
-	const float2 pre0 = __ldg(x.pretw + tid); // exp(-i*pi*tid/N); element tid + 256*it gets a compile-time factor on top
 	const int PJ = g.C * x.maxFrames;         // pair slots per stream (2*C*maxFrames jobs)
 	const long long total = (long long)x.sCount * PJ;
 
@@ -92,6 +91,24 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 	while (item < total) {
 		float2 *dstA = x.spec + ((size_t)cur.s * 2 * x.maxFrames * g.C + cur.a.row) * g.K;
 		float2 *dstB = x.spec + ((size_t)cur.s * 2 * x.maxFrames * g.C + cur.b.row) * g.K;
+		// window samples and pre-twiddles of this thread's R3 elements: issued before the wait so that their latency overlaps it.
+		// (The values are the same for every pair; `wofs` is opaque to the compiler so that they are re-loaded,
+		// L1/L2 hits, instead of being hoisted into 2*R3 permanently live registers.)
+		float w0r[G::R3], w1r[G::R3];
+		float2 prer[G::R3]; // half-bin pre-twiddles exp(-i*pi*n/N) of the same elements
+		{
+			int wofs = 0;
+#ifndef B200S_EMU
+			asm volatile("" : "+r"(wofs));
+#endif
+			static_for<G::R3>([&](auto itc) {
+				constexpr int it = decltype(itc)::value;
+				const int i0 = tid + 256 * it + o, i1 = i0 - KT;
+				w0r[it] = i0 < B ? __ldg(x.window + i0 + wofs) : 0.f;
+				w1r[it] = i1 >= 0 ? __ldg(x.window + i1 + wofs) : 0.f;
+				prer[it] = __ldg(x.pretw + tid + 256 * it + wofs);
+			});
+		}
 		cp_async_wait_all();
 		__syncthreads(); // staging complete and visible; previous unpack finished with buf
 #ifdef B200S_EMU_EXACT_FFT // test builds only: swap in the oracle's double FFT to isolate the non-FFT logic
@@ -130,12 +147,10 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 				constexpr int it = decltype(itc)::value;
 				const int n = tid + 256 * it, i0 = n + o, i1 = n + o - KT;
 				const bool in0 = i0 < B, in1 = i1 >= 0;
-				const float w0 = in0 ? __ldg(x.window + i0) : 0.f, w1 = in1 ? __ldg(x.window + i1) : 0.f;
+				const float w0 = w0r[it], w1 = w1r[it];
 				const float a0 = in0 ? stA[i0 + shA] : 0.f, a1 = in1 ? stA[i1 + shA] : 0.f;
 				const float b0 = in0 ? stB[i0 + shB] : 0.f, b1 = in1 ? stB[i1 + shB] : 0.f;
-				// exp(-i*pi*n/N) = pre0 * exp(-i*pi*256*it/N), the second factor is a compile-time constant
-				constexpr float fc = float(ct::cosq(256 * it, 4 * KT)), fs = -float(ct::sinq(256 * it, 4 * KT));
-				const float2 pw = cmulf(pre0, make_float2(fc, fs));
+				const float2 pw = prer[it]; // exp(-i*pi*n/N), exactly rounded table entry
 				const c2 t = c2{muls(f2_make(a0, b0), w0), muls(f2_make(a1, b1), w1)}; // (x0*w0) + i*(x1*w1)
 				v[it] = cmulw(t, pw.x, pw.y);
 			});
@@ -255,27 +270,38 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 		}
 		__syncthreads();
 #else
+		float *yTimeA = (float *)buf, *yTimeB = yTimeA + B; // the FFT buffer is reused for the real time-domain blocks
 		if (tid < G::M1) pair_dif_pass1<KT>(buf, tw, tid, v);
 		__syncthreads(); // buf complete; the emission above is complete too
-		pair_dif_pass23<KT>(buf, tw, tid);
+		{
+			// last pass in registers, then the half-bin post-twiddle: time sample i of the block is
+			// 2*Re(z[i-o] * conj(pre[i-o])) for i >= o and 2*Im(z[i-o+K] * conj(pre[i-o+K])) for i < o,
+			// so z[n2] yields sample n2+o (if < B) from its real part and sample n2+o-K (if >= 0) from its imaginary part
+			c2 z[G::R3];
+			pair_dif_pass23<KT>(buf, tw, tid, z);
+			__syncthreads(); // every thread has its outputs in registers: the buffer can take the real samples
+			static_for<G::R3>([&](auto qc) {
+				constexpr int q3 = decltype(qc)::value;
+				const int n2 = (tid & 15) + 16 * (tid >> 4) + 256 * q3;
+				const float2 pw = __ldg(x.pretw + n2);
+				const int iRe = n2 + o, iIm = n2 + o - KT;
+				if (iRe < B) {
+					const f2 y = muls(fmas(z[q3].im, pw.y, muls(z[q3].re, pw.x)), 2.f);
+					yTimeA[iRe] = f2_lo(y);
+					yTimeB[iRe] = f2_hi(y);
+				}
+				if (iIm >= 0) {
+					const f2 y = muls(fmas(z[q3].re, -pw.y, muls(z[q3].im, pw.x)), 2.f);
+					yTimeA[iIm] = f2_lo(y);
+					yTimeB[iIm] = f2_hi(y);
+				}
+			});
+			__syncthreads();
+		}
 #endif
 		// ---- one sweep over the ring: slot j ahead of the head gets, in the reference's order,
 		//      block A's sample j-addOff, the emission if j < gap, then block B's sample (relative to the new head)
-		// windowed synthesis output sample i of transform `which`: w[i] * 2*Re/Im(z[n2] * conj(pre[n2]))
-		auto contrib = [&](int i, bool second) -> float {
-			const float w = __ldg(x.window + i);
-#ifdef B200S_EMU_EXACT_FFT
-			return fmul((second ? yTimeB : yTimeA)[i], w);
-#else
-			const bool hi = i >= o;
-			const int n2 = hi ? i - o : i - o + KT;
-			const float4 z = buf[G::slot_rev(n2)];
-			const float2 p = __ldg(x.pretw + n2);
-			const float re = second ? z.y : z.x, im = second ? z.w : z.z;
-			const float y = hi ? (re * p.x + im * p.y) : (im * p.x - re * p.y);
-			return fmul(2.f * y, w);
-#endif
-		};
+		auto contrib = [&](int i, bool second) -> float { return fmul((second ? yTimeB : yTimeA)[i], __ldg(x.window + i)); };
 		for (int j = tid; j < P; j += 256) {
 			int p = head + j;
 			if (p >= P) p -= P;
