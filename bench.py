@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="streams per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sub-batches", type=int, default=0, help="device-resident path: split the batch over N prioritised CUDA streams (experiment)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4], help="BASELINE config (default 2 = the headline)")
     args = ap.parse_args()
     if args.config != 2:
@@ -248,6 +249,8 @@ def main():
             eng.setFormantFactor(1.0, True)
             eng.setFormantBase(200.0 / SR)
     eng.reserve(w["n_in"], w["n_out"])
+    if args.sub_batches > 1:
+        eng.set_sub_batches(args.sub_batches)
 
     # three distinct input buffers (each >> L2), consecutive seconds of each stream's audio
     x_host = synth_input(args.batch, 3 * w["n_in"], seed0=lo)

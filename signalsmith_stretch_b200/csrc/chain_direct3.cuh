@@ -30,9 +30,11 @@ namespace b200s {
 
 struct Chain3Tiles {
 	float4 in[CH3_RING][CH3_RS]; // rolling window of each block's interleaved input spectrum, [bin & 31][lane]
-	float4 pvy[CHAIN_CH][CH3_RS]; // previous-input spectrum at the chunk's bins; overwritten by the finals of the same step
-	float4 p0Out[CHAIN_CH];       // lane 0's predecessor block: {c0.re, c0.im, c1.re, c1.im}
-	float2 p0E[CHAIN_CH];         // its Prediction::energy {c0, c1}
+	// previous-input spectrum at the chunk's bins; overwritten by the finals of the same step.  Two buffers: the
+	// fill of chunk c+1 is in flight (cp.async) while chunk c is computed
+	float4 pvy[2][CHAIN_CH][CH3_RS];
+	float4 p0Out[2][CHAIN_CH];    // lane 0's predecessor block: {c0.re, c0.im, c1.re, c1.im}
+	float2 p0E[2][CHAIN_CH];      // its Prediction::energy {c0, c1}
 	const float4 *rowIn[32], *rowPv[32];
 	float2 *rowY[32]; // channel 0 row of Band::output; channel 1 row follows K bins later
 };
@@ -145,7 +147,6 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 		const Frame fr = x.frames[(size_t)s * x.maxFrames + (active ? f : base)];
 		const bool rotOn = fr.flags & FR_NEW_SPECTRUM;
 		const int nAct = min(32, cl.nFrames - base);
-		const bool carryE = active && (lane == 31 || f == cl.nFrames - 1); // Prediction::energy needed later
 		const float tf = fmaxf(fr.timeFactor, 1.0f / B200S_MAX_CLEAN_STRETCH); // :638
 		const float longTf = fmul((float)LT, tf);
 		const bool farAny = __any_sync(0xffffffffu, active && longTf > (float)(CH3_RING - CHAIN_CH - 3));
@@ -154,10 +155,12 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 #pragma unroll
 		for (int c = 0; c < 2; ++c) {
 			prevOut[c] = base == 0 ? x.stOut + ((size_t)s * 2 + c) * K : x.Y + coef_off(x, s, base - 1, c);
-			prevE[c] = base == 0 ? x.stPredE + ((size_t)s * 2 + c) * K : x.cE + coef_off(x, s, base - 1, c);
+			prevE[c] = x.stPredE + ((size_t)s * 2 + c) * K; // base == 0 only; later groups recompute it, see the fill
 		}
+		// Prediction::energy of a block on this path is |input|^2 of its own spectrum (:679,:708): the chain never stores
+		// it -- the next group recomputes it from the predecessor's input row, k_commit from the final input spectrum
+		const float4 *prevIn = base == 0 ? nullptr : il_row(x, s, x.frames[(size_t)s * x.maxFrames + base - 1].inSlot);
 		const float4 *myIn = il_row(x, s, fr.inSlot);
-		float *myE = x.cE + coef_off(x, s, active ? f : base, 0); // channel 1: + K
 		U.rowIn[lane] = myIn;
 		U.rowPv[lane] = il_row(x, s, fr.prevSlot);
 		U.rowY[lane] = x.Y + coef_off(x, s, active ? f : base, 0);
@@ -185,26 +188,38 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 			for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
 			interiorFrom = D * (nAct - 1) + 2 * LT + (int)ceilf(mx) + 2;
 		}
-		for (int k0 = 0; k0 < steps; k0 += CHAIN_CH) {
-			// ---------------- stage the chunk: 8 new bins per block, both channels per 16-byte copy ----------------
+		// asynchronous fill of the chunk starting at kf into buffer `buf`: 8 new bins per block, both channels per
+		// 16-byte copy.  The ring slots it writes ((q .. q+7) & 31 per lane) are disjoint from what the chunk in
+		// progress reads (at most L*tf + 1 <= 9 bins behind its own 8).
+		auto fill = [&](int kf, int buf) {
 #pragma unroll
 			for (int it = 0; it < 8; ++it) {
 				const int fl = fillF + 4 * it;
-				const int q = k0 + fillI - D * fl;
+				const int q = kf + fillI - D * fl;
 				if (base + fl < cl.nFrames && (unsigned)q < (unsigned)K) {
 					cp_async16(&U.in[q & (CH3_RING - 1)][fl], U.rowIn[fl] + q);
-					cp_async16(&U.pvy[fillI][fl], U.rowPv[fl] + q);
+					cp_async16(&U.pvy[buf][fillI][fl], U.rowPv[fl] + q);
 				}
 			}
 			if (lane < 2 * CHAIN_CH) { // lane 0's predecessor: planar state / previous group rows -> {c0, c1} slots
-				const int qq = k0 + (lane >> 1), c = lane & 1;
+				const int qq = kf + (lane >> 1), c = lane & 1;
 				if (qq < K) {
-					cp_async8((float2 *)&U.p0Out[lane >> 1] + c, (c ? prevOut[1] : prevOut[0]) + qq);
-					cp_async4((float *)&U.p0E[lane >> 1] + c, (c ? prevE[1] : prevE[0]) + qq);
+					cp_async8((float2 *)&U.p0Out[buf][lane >> 1] + c, (c ? prevOut[1] : prevOut[0]) + qq);
+					if (base == 0) {
+						cp_async4((float *)&U.p0E[buf][lane >> 1] + c, (c ? prevE[1] : prevE[0]) + qq);
+					} else {
+						const float4 v = prevIn[qq];
+						((float *)&U.p0E[buf][lane >> 1])[c] = c ? xnorm(make_float2(v.y, v.w)) : xnorm(make_float2(v.x, v.z));
+					}
 				}
 			}
-			cp_async_wait_all();
+		};
+		fill(0, 0);
+		int cb = 0; // buffer of the chunk being computed
+		for (int k0 = 0; k0 < steps; k0 += CHAIN_CH, cb ^= 1) {
+			cp_async_wait_all(); // this chunk's tiles (issued one chunk ago)
 			__syncwarp();
+			if (k0 + CHAIN_CH < steps) fill(k0 + CHAIN_CH, cb ^ 1); // next chunk: in flight during the 8 steps below
 			// ---------------- CHAIN_CH steps ----------------
 			// INTERIOR: every lane's q, b and interpolation points are inside [0, K) for the whole chunk, so all the
 			// edge masks below are identities and are compiled out (about nine chunks in ten)
@@ -213,7 +228,6 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 				const int q = k0 + i - D * lane;
 				const int b = q - LT;
 				const bool qIn = INTERIOR || (active && (unsigned)q < (unsigned)K);
-				const bool bIn = INTERIOR ? active : (active && (unsigned)b < (unsigned)K);
 				// the twists need input interpolated at q - L*tf and (b+1) - tf  (:750,:757)
 				const float i2 = fsub((float)q, longTf);
 				const int l2 = (int)floorf(i2);
@@ -228,14 +242,14 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 					const float a0 = __shfl_up_sync(0xffffffffu, f2_lo(lastFinal.re), 1), a1 = __shfl_up_sync(0xffffffffu, f2_hi(lastFinal.re), 1);
 					const float b0 = __shfl_up_sync(0xffffffffu, f2_lo(lastFinal.im), 1), b1 = __shfl_up_sync(0xffffffffu, f2_hi(lastFinal.im), 1);
 					const float e0 = __shfl_up_sync(0xffffffffu, f2_lo(lastE), 1), e1 = __shfl_up_sync(0xffffffffu, f2_hi(lastE), 1);
-					const float4 p0 = U.p0Out[i];
-					const float2 p0e = U.p0E[i];
+					const float4 p0 = U.p0Out[cb][i];
+					const float2 p0e = U.p0E[cb][i];
 					const bool first = lane == 0;
 					ro = c2{f2_make(first ? p0.x : a0, first ? p0.z : a1), f2_make(first ? p0.y : b0, first ? p0.w : b1)};
 					re = f2_make(first ? p0e.x : e0, first ? p0e.y : e1);
 				}
 				const c2 inq = ld_c2s(&U.in[q & (CH3_RING - 1)][lane]);
-				c2 pv = ld_c2s(&U.pvy[i][lane]);
+				c2 pv = ld_c2s(&U.pvy[cb][i][lane]);
 				c2 lo2, hi2, lo1, hi1;
 				if constexpr (!FAR) {
 					lo2 = sel_c2(INTERIOR || l2 >= 0, ld_c2s(&U.in[l2 & (CH3_RING - 1)][lane]));
@@ -303,11 +317,7 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 				lastFinal = oc;
 				lastE = eB;
 				t1P = t1N;
-				if (carryE && bIn) {
-					myE[b] = f2_lo(eB);
-					myE[K + b] = f2_hi(eB);
-				}
-				U.pvy[i][lane] = make_float4(f2_lo(oc.re), f2_hi(oc.re), f2_lo(oc.im), f2_hi(oc.im));
+				U.pvy[cb][i][lane] = make_float4(f2_lo(oc.re), f2_hi(oc.re), f2_lo(oc.im), f2_hi(oc.im));
 			};
 			// unrolled by 4 (for L = 4 the register FIFOs rotate by pure renaming) so that the hot loop stays in the
 			// instruction cache; branch-free inside
@@ -328,7 +338,7 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 				const int fl = fillF + 4 * it;
 				const int b = k0 + fillI - D * fl - LT;
 				if (base + fl < cl.nFrames && (unsigned)b < (unsigned)K) {
-					const float4 v = U.pvy[fillI][fl];
+					const float4 v = U.pvy[cb][fillI][fl];
 					U.rowY[fl][b] = make_float2(v.x, v.z);
 					U.rowY[fl][K + b] = make_float2(v.y, v.w);
 				}

@@ -103,6 +103,7 @@ struct Ctx {
 	// tables
 	const float *window, *winProd, *wpReset;
 	const float2 *rot, *twiddle, *pretw;
+	const float4 *anaTab; // [K] {window[n+o], window[n+o-K], pretw[n].x, pretw[n].y}: one load per element in k_analyse2
 	float2 rot0, rotStep; // rot[b+1] = rot[b] * rotStep in float, the reference's own recurrence (:647-655)
 	// state
 	Sched *sched;

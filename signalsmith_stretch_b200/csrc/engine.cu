@@ -52,6 +52,7 @@ struct b200s_engine {
 	// tables
 	float *dWindow = 0, *dWinProd = 0, *dWpReset = 0;
 	float2 *dRot = 0, *dTwiddle = 0, *dPretw = 0;
+	float4 *dAnaTab = 0;
 	float2 rot0, rotStep;
 	float *dMapIn = 0, *dMapOut = 0;
 	// state
@@ -111,7 +112,7 @@ static void dfree(T *&p) {
 }
 
 static void free_all(b200s_engine *e) {
-	dfree(e->dWindow); dfree(e->dWinProd); dfree(e->dWpReset); dfree(e->dRot); dfree(e->dTwiddle); dfree(e->dPretw);
+	dfree(e->dWindow); dfree(e->dWinProd); dfree(e->dWpReset); dfree(e->dRot); dfree(e->dTwiddle); dfree(e->dPretw); dfree(e->dAnaTab);
 	dfree(e->dSched); dfree(e->dHist[0]); dfree(e->dHist[1]); dfree(e->dPend); dfree(e->dPendWp);
 	dfree(e->dStIn); dfree(e->dStPrev); dfree(e->dStOut); dfree(e->dStPredE); dfree(e->dStIl);
 	dfree(e->dFrames); dfree(e->dCall); dfree(e->dJobs); dfree(e->dSpec); dfree(e->dY); dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dE);
@@ -128,7 +129,7 @@ static Ctx make_ctx(b200s_engine *e) {
 	x.prm.mapIn = e->dMapIn;
 	x.prm.mapOut = e->dMapOut;
 	x.window = e->dWindow; x.winProd = e->dWinProd; x.wpReset = e->dWpReset;
-	x.rot = e->dRot; x.twiddle = e->dTwiddle; x.pretw = e->dPretw;
+	x.rot = e->dRot; x.twiddle = e->dTwiddle; x.pretw = e->dPretw; x.anaTab = e->dAnaTab;
 	x.rot0 = e->rot0; x.rotStep = e->rotStep;
 	x.one = 1.0f;
 	x.sched = e->dSched;
@@ -387,6 +388,15 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	CK(cudaMemcpy(e->dRot, rot.data(), sizeof(float2) * g.K, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(e->dTwiddle, tw.data(), sizeof(float2) * g.K, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(e->dPretw, pre.data(), sizeof(float2) * g.K, cudaMemcpyHostToDevice));
+	{ // per-element constants of the analysis load stage, one float4 each
+		std::vector<float4> tab(g.K);
+		for (int n = 0; n < g.K; ++n) {
+			const int i0 = n + g.o, i1 = n + g.o - g.K;
+			tab[n] = make_float4(i0 < g.B ? window[i0] : 0.f, i1 >= 0 ? window[i1] : 0.f, pre[n].x, pre[n].y);
+		}
+		if ((rc = dalloc(e, &e->dAnaTab, g.K))) return rc;
+		CK(cudaMemcpy(e->dAnaTab, tab.data(), sizeof(float4) * g.K, cudaMemcpyHostToDevice));
+	}
 
 	// ---- state
 	const size_t SC = (size_t)g.S * g.C;

@@ -94,8 +94,7 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 		// window samples and pre-twiddles of this thread's R3 elements: issued before the wait so that their latency overlaps it.
 		// (The values are the same for every pair; `wofs` is opaque to the compiler so that they are re-loaded,
 		// L1/L2 hits, instead of being hoisted into 2*R3 permanently live registers.)
-		float w0r[G::R3], w1r[G::R3];
-		float2 prer[G::R3]; // half-bin pre-twiddles exp(-i*pi*n/N) of the same elements
+		float4 tabr[G::R3]; // {window[n+o], window[n+o-K], pre-twiddle exp(-i*pi*n/N)} of element n = tid + 256*it
 		{
 			int wofs = 0;
 #ifndef B200S_EMU
@@ -103,10 +102,7 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 #endif
 			static_for<G::R3>([&](auto itc) {
 				constexpr int it = decltype(itc)::value;
-				const int i0 = tid + 256 * it + o, i1 = i0 - KT;
-				w0r[it] = i0 < B ? __ldg(x.window + i0 + wofs) : 0.f;
-				w1r[it] = i1 >= 0 ? __ldg(x.window + i1 + wofs) : 0.f;
-				prer[it] = __ldg(x.pretw + tid + 256 * it + wofs);
+				tabr[it] = __ldg(x.anaTab + tid + 256 * it + wofs);
 			});
 		}
 		cp_async_wait_all();
@@ -147,10 +143,10 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 				constexpr int it = decltype(itc)::value;
 				const int n = tid + 256 * it, i0 = n + o, i1 = n + o - KT;
 				const bool in0 = i0 < B, in1 = i1 >= 0;
-				const float w0 = w0r[it], w1 = w1r[it];
+				const float w0 = tabr[it].x, w1 = tabr[it].y;
 				const float a0 = in0 ? stA[i0 + shA] : 0.f, a1 = in1 ? stA[i1 + shA] : 0.f;
 				const float b0 = in0 ? stB[i0 + shB] : 0.f, b1 = in1 ? stB[i1 + shB] : 0.f;
-				const float2 pw = prer[it]; // exp(-i*pi*n/N), exactly rounded table entry
+				const float2 pw = make_float2(tabr[it].z, tabr[it].w); // exp(-i*pi*n/N), exactly rounded table entry
 				const c2 t = c2{muls(f2_make(a0, b0), w0), muls(f2_make(a1, b1), w1)}; // (x0*w0) + i*(x1*w1)
 				v[it] = cmulw(t, pw.x, pw.y);
 			});
