@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="streams per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs (ncu): device-resident steps only; the JSON line then has no e2e / per-kernel split")
     ap.add_argument("--sub-batches", type=int, default=0, help="device-resident path: split the batch over N prioritised CUDA streams (experiment)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4], help="BASELINE config (default 2 = the headline)")
     args = ap.parse_args()
@@ -283,6 +284,14 @@ def main():
     clk = clocks.stop()
     total, tmax = reduce_throughput(w["samples_per_step"] * args.steps, ms / 1e3, dist if world > 1 else None, dev)
     value = total / tmax
+
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                              "ms_per_step": tmax / args.steps * 1e3, "gpu_launches": int(launches), "note": "--no-e2e profiling run"}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the host-buffer C ABI: pinned host in, pinned host out, copies timed
     for i in range(2):

@@ -51,7 +51,7 @@ int b200s_synchronize(b200s_engine *e);
  * different kernels of its launch sequence overlap (default 1 = off). */
 int b200s_set_sub_batches(b200s_engine *e, int n);
 /* Implementation selectors for A/B measurement and cross-checking (results are identical by contract):
- *   key 0: direct chain kernel generation (1, 2, 3; 0 = default)   key 1: FFT kernels (1 = scalar Stockham, 0 = default paired)
+ *   key 0: direct chain kernel generation (1..4; 0 = default)   key 1: FFT kernels (1 = scalar Stockham, 0 = default paired)
  *   key 2: stream groups of the host-buffer pipeline in b200s_process (1..8) */
 int b200s_set_tuning(b200s_engine *e, int key, int value);
 

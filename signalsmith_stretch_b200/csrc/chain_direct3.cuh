@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 		const int nAct = min(32, cl.nFrames - base);
 		const float tf = fmaxf(fr.timeFactor, 1.0f / B200S_MAX_CLEAN_STRETCH); // :638
 		const float longTf = fmul((float)LT, tf);
-		const bool farAny = __any_sync(0xffffffffu, active && longTf > (float)(CH3_RING - CHAIN_CH - 3));
+		const bool farAny = __any_sync(0xffffffffu, active && longTf > (float)(CH3_RING - 2 * CHAIN_CH - 3)); // 8 bins of the next chunk are in flight
 		const float2 *prevOut[2];
 		const float *prevE[2];
 #pragma unroll

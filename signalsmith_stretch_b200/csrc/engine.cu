@@ -21,6 +21,7 @@
 #include "chain_direct2.cuh"
 #include "stft2.cuh"
 #include "chain_direct3.cuh"
+#include "chain_direct4.cuh"
 
 using namespace b200s;
 
@@ -238,11 +239,21 @@ static int chain_version(const Cfg &g, int override, int forceFftV1) {
 		const char *v = getenv("B200S_CHAIN_V");
 		env = v ? atoi(v) : 0;
 	}
-	int want = override ? override : env ? env : 3;
-	if (want == 3 && !(g.C == 2 && use_pair_fft(g, forceFftV1))) want = 2;
+	int want = override ? override : env ? env : 4;
+	if (want >= 3 && !(g.C == 2 && use_pair_fft(g, forceFftV1))) want = 2;
 	return want;
 }
-static ChainKernel chain3_kernel(const Cfg &g) {
+static ChainKernel chain3_kernel(const Cfg &g, int v) {
+	if (v == 4) switch (g.L) {
+		case 1: return k_chain_direct4<1>;
+		case 2: return k_chain_direct4<2>;
+		case 3: return k_chain_direct4<3>;
+		case 4: return k_chain_direct4<4>;
+		case 5: return k_chain_direct4<5>;
+		case 6: return k_chain_direct4<6>;
+		case 7: return k_chain_direct4<7>;
+		default: return k_chain_direct4<8>;
+		}
 	switch (g.L) {
 	case 1: return k_chain_direct3<1>;
 	case 2: return k_chain_direct3<2>;
@@ -510,7 +521,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	const bool plain = !(e->prm.mapN > 0 || e->prm.freqMultiplier != 1.0f) && e->prm.formantMultiplier == 1.0f;
 	const int chainV = chain_version(g, e->chainV, e->fftV1);
 	const bool pairFft = use_pair_fft(g, e->fftV1);
-	x.specIl = (plain && chainV == 3) ? 1 : 0;
+	x.specIl = (plain && chainV >= 3) ? 1 : 0;
 	for (int sub = 0; sub < nSub; ++sub) {
 		cudaStream_t st = nSub > 1 ? e->subStream[sub] : e->stream;
 		if (nSub > 1) CK(cudaStreamWaitEvent(st, e->evBegin, 0));
@@ -532,8 +543,8 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 				// Pure time-stretch (no frequency map, no formants): the chain forms its terms directly from
 				// the spectra and k_prep is skipped; otherwise k_prep produces the coefficient arrays.
 				if (!plain) PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g), st, x));
-				if (plain && chainV == 3) {
-					PROF(PK_CHAIN, B200S_LAUNCH(chain3_kernel(g), dim3(x.sCount), dim3(32), sizeof(Chain3Tiles), st, x));
+				if (plain && chainV >= 3) {
+					PROF(PK_CHAIN, B200S_LAUNCH(chain3_kernel(g, chainV), dim3(x.sCount), dim3(32), chainV == 4 ? smem_chain4(g.L) : sizeof(Chain3Tiles), st, x));
 				} else if (plain && chainV == 2) {
 					const int W = chain2_warps(g, nOut);
 					ChainKernel kc = chain2_kernel(g);
@@ -722,7 +733,7 @@ int b200s_set_sub_batches(b200s_engine *e, int n) {
 }
 int b200s_set_tuning(b200s_engine *e, int key, int value) {
 	if (!e) return B200S_EINVAL;
-	if (key == 0 && value >= 0 && value <= 3) e->chainV = value;
+	if (key == 0 && value >= 0 && value <= 4) e->chainV = value;
 	else if (key == 1 && (value == 0 || value == 1)) e->fftV1 = value;
 	else if (key == 2 && value >= 1) e->nHostParts = std::min(value, (int)b200s_engine::kMaxSub);
 	else {

@@ -27,6 +27,20 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
 
 __host__ __device__ __forceinline__ int stage_len(int B) { return (B + 8 + 3) & ~3; }
 
+// streaming accesses (read once / written once): keep them out of L1, which -- next to two 95 KB CTAs -- is only
+// large enough for the window / twiddle tables that every item re-reads
+#ifdef B200S_EMU
+__device__ __forceinline__ float2 ld_stream(const float2 *p) { return *p; }
+__device__ __forceinline__ void st_stream(float *p, float v) { *p = v; }
+#else
+__device__ __forceinline__ float2 ld_stream(const float2 *p) {
+	float2 v;
+	asm volatile("ld.global.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ void st_stream(float *p, float v) { __stcs(p, v); }
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // k_analyse2: grid = persistent CTAs (a multiple of the SM count), 256 threads.
 // dyn smem: PairGeo::LEN float4 (FFT pair) + 2 * stage_len(B) floats (raw samples of the next pair).
@@ -48,46 +62,68 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 		Job a, b;
 	};
 	// item -> jobs; false when the stream has fewer pairs than slots
+	// (the three loads are independent of each other: the job slots exist even when the stream has fewer jobs)
 	auto fetch = [&](long long it, Item &m) -> bool {
 		m.s = x.sBase + (int)(it / PJ);
 		const int p = (int)(it % PJ), nJ = x.call[m.s].nJobs;
-		if (2 * p >= nJ) return false;
 		const Job *jb = x.jobs + (size_t)m.s * 2 * g.C * x.maxFrames + 2 * p;
 		m.a = jb[0];
+		m.b = jb[1];
 		m.hasB = 2 * p + 1 < nJ;
-		m.b = m.hasB ? jb[1] : jb[0];
-		return true;
+		if (!m.hasB) m.b = m.a;
+		return 2 * p < nJ;
 	};
 	auto next_valid = [&](long long it, Item &m) -> long long {
 		while (it < total && !fetch(it, m)) it += gridDim.x;
 		return it;
 	};
-	// asynchronously copy the B samples (history ++ input) of one job into a staging buffer;
-	// aligned mode copies 16-byte chunks of the enclosing 4-aligned range (sample i lands at st[i + (start & 3)])
-	auto stage_job = [&](float *st, int s, const Job &j) {
+	// asynchronously copy the B samples (history ++ input) of one job into a staging buffer.
+	// Aligned mode copies the enclosing 4-aligned range (sample i lands at st[i + (start & 3)]) with at most two BULK
+	// copies issued by one thread -- the part that lies in the history and the part that lies in this call's input --
+	// which complete on the CTA's mbarrier (two arrivals per item: one per job); whatever lies outside both (before the
+	// history, after the input) is zero-filled by all threads.  (The per-16-byte cp.async loop this replaces was 17 % of
+	// the kernel's instructions, profiles/r01_v12.)
+	B200S_SHARED unsigned long long stageBar;
+	if (tid == 0) mbar_init(&stageBar, 2);
+	fence_async_proxy();
+	__syncthreads();
+	unsigned stagePar = 0u;
+	auto stage_job = [&](float *st, int s, const Job &j, int t0, int nT) {
 		const float *ib = x.in + (size_t)s * x.inStreamStride + (size_t)j.c * x.inChanStride;
 		const float *he = x.histCur + ((size_t)s * g.C + j.c) * g.histLen + g.histLen;
 		if (x.inAligned) {
 			const int sh = j.start & 3, a00 = j.start - sh, nCh = (B + sh + 3) >> 2;
-			for (int q = tid; q < nCh; q += 256) {
-				const int a0 = a00 + 4 * q;
-				if (a0 >= 0 ? (a0 < x.nIn) : (a0 >= -g.histLen)) cp_async16(st + 4 * q, a0 >= 0 ? ib + a0 : he + a0);
-				else *(float4 *)(st + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+			// chunk q holds samples a00 + 4q ..: [qh0, z) comes from the history, [z, qi1) from the input
+			const int z = min(max((-a00) >> 2, 0), nCh);
+			const int qh0 = min(max((-g.histLen - a00) >> 2, 0), z), qi1 = min(max((x.nIn - a00) >> 2, z), nCh);
+			if (tid == t0) {
+				fence_async_proxy(); // the staging buffer was last read through the generic proxy
+				mbar_expect(&stageBar, 16u * (unsigned)(qi1 - qh0));
+				if (z > qh0) bulk_g2s(st + 4 * qh0, he + a00 + 4 * qh0, 16u * (unsigned)(z - qh0), &stageBar);
+				if (qi1 > z) bulk_g2s(st + 4 * z, ib + a00 + 4 * z, 16u * (unsigned)(qi1 - z), &stageBar);
 			}
+			for (int q = tid; q < qh0; q += 256) *(float4 *)(st + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+			for (int q = qi1 + tid; q < nCh; q += 256) *(float4 *)(st + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
 		} else {
-			for (int i = tid; i < B; i += 256) {
+			for (int i = tid; i < B; i += nT) {
 				const int a = j.start + i;
 				if (a < x.nIn && a >= -g.histLen) cp_async4(st + i, a >= 0 ? ib + a : he + a);
 				else st[i] = 0.f;
 			}
 		}
 	};
+	// Items are looked up TWO iterations ahead: the descriptor loads of the item after next are issued while the
+	// current pair is transformed and are only consumed at the end of the iteration, so that the copies of the next
+	// item's input can start the moment the staging buffers are free.  (Measured alternative, profiles/r01_v12: letting
+	// the two warps that idle during the radix-16 passes do the look-up and the copies was slower -- the other six
+	// waited for them at the next barrier.)
 	Item cur, nxt;
 	long long item = next_valid(blockIdx.x, cur);
 	if (item < total) {
-		stage_job(stA, cur.s, cur.a);
-		stage_job(stB, cur.s, cur.b);
+		stage_job(stA, cur.s, cur.a, 0, 256);
+		stage_job(stB, cur.s, cur.b, 32, 256);
 	}
+	long long nitem = item < total ? next_valid(item + gridDim.x, nxt) : total;
 	while (item < total) {
 		float2 *dstA = x.spec + ((size_t)cur.s * 2 * x.maxFrames * g.C + cur.a.row) * g.K;
 		float2 *dstB = x.spec + ((size_t)cur.s * 2 * x.maxFrames * g.C + cur.b.row) * g.K;
@@ -106,6 +142,10 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 			});
 		}
 		cp_async_wait_all();
+		if (x.inAligned) {
+			mbar_wait(&stageBar, stagePar);
+			stagePar ^= 1u;
+		}
 		__syncthreads(); // staging complete and visible; previous unpack finished with buf
 #ifdef B200S_EMU_EXACT_FFT // test builds only: swap in the oracle's double FFT to isolate the non-FFT logic
 		{
@@ -126,12 +166,13 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 				}
 			}
 			__syncthreads();
-			item = next_valid(item + gridDim.x, nxt);
-			if (item < total) {
-				stage_job(stA, nxt.s, nxt.a);
-				stage_job(stB, nxt.s, nxt.b);
-			}
+			item = nitem;
 			cur = nxt;
+			if (item < total) {
+				stage_job(stA, cur.s, cur.a, 0, 256);
+				stage_job(stB, cur.s, cur.b, 32, 256);
+				nitem = next_valid(item + gridDim.x, nxt);
+			}
 			continue;
 		}
 #endif
@@ -155,10 +196,13 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 			static_for<G::R3>([&](auto qc) { st_c2(p + decltype(qc)::value, v[decltype(qc)::value]); });
 		}
 		__syncthreads(); // staging consumed, buf complete
-		const long long nitem = next_valid(item + gridDim.x, nxt);
+		Item n2;
+		long long cand = nitem + gridDim.x;
+		bool ok2 = false;
 		if (nitem < total) { // start the next pair's input on its way while this FFT runs
-			stage_job(stA, nxt.s, nxt.a);
-			stage_job(stB, nxt.s, nxt.b);
+			stage_job(stA, nxt.s, nxt.a, 0, 256);
+			stage_job(stB, nxt.s, nxt.b, 32, 256);
+			if (cand < total) ok2 = fetch(cand, n2); // descriptor of the item after next: loads in flight until the end of the iteration
 		}
 		pair_dit_stage_b<KT>(buf, tw, tid);
 		__syncthreads();
@@ -185,6 +229,11 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 		}
 		item = nitem;
 		cur = nxt;
+		if (nitem < total) {
+			if (cand < total && !ok2) cand = next_valid(cand + gridDim.x, n2); // rare: a stream with fewer pairs than slots
+			nitem = cand < total ? cand : total;
+			nxt = n2;
+		}
 	}
 }
 
@@ -230,7 +279,7 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 				pend[p] = 0.f;
 				wp[p] = B200S_ALMOST_ZERO;
 			}
-			out[emitted + i] = v;
+			st_stream(out + emitted + i, v);
 		}
 		head = (head + (n < P ? n : P)) % P; // n >= P leaves an all-clear ring; any head is fine
 		emitted += n;
@@ -251,7 +300,7 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 				const int k = q * G::M1 + tid;
 				const int b = q < 8 ? 2 * k : 2 * (KT - 1 - k) + 1;
 				const float sg = q < 8 ? 1.f : -1.f;
-				const float2 a = YA[b], bb = YB[b];
+				const float2 a = ld_stream(YA + b), bb = ld_stream(YB + b);
 				v[q] = c2{f2_make(a.x, bb.x), f2_make(sg * a.y, sg * bb.y)};
 			});
 		}
@@ -263,6 +312,10 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 		if (tid == 0) {
 			emu_exact_inverse(YA, B, o, g.N, yTimeA);
 			if (hasB) emu_exact_inverse(YB, B, o, g.N, yTimeB);
+			for (int i = 0; i < B; ++i) { // the synthesis window is applied where the block is written (see below)
+				yTimeA[i] = fmul(yTimeA[i], x.window[i]);
+				if (hasB) yTimeB[i] = fmul(yTimeB[i], x.window[i]);
+			}
 		}
 		__syncthreads();
 #else
@@ -279,15 +332,17 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 			static_for<G::R3>([&](auto qc) {
 				constexpr int q3 = decltype(qc)::value;
 				const int n2 = (tid & 15) + 16 * (tid >> 4) + 256 * q3;
-				const float2 pw = __ldg(x.pretw + n2);
+				// one 16-byte table entry per element: {window[n2+o], window[n2+o-K], pre-twiddle}; the synthesis window
+				// (:397-399, y * window) is applied here, where the index is fixed per thread, not in the ring sweep
+				const float4 tb = __ldg(x.anaTab + n2);
 				const int iRe = n2 + o, iIm = n2 + o - KT;
 				if (iRe < B) {
-					const f2 y = muls(fmas(z[q3].im, pw.y, muls(z[q3].re, pw.x)), 2.f);
+					const f2 y = muls(muls(fmas(z[q3].im, tb.w, muls(z[q3].re, tb.z)), 2.f), tb.x);
 					yTimeA[iRe] = f2_lo(y);
 					yTimeB[iRe] = f2_hi(y);
 				}
 				if (iIm >= 0) {
-					const f2 y = muls(fmas(z[q3].re, -pw.y, muls(z[q3].im, pw.x)), 2.f);
+					const f2 y = muls(muls(fmas(z[q3].re, -tb.w, muls(z[q3].im, tb.z)), 2.f), tb.y);
 					yTimeA[iIm] = f2_lo(y);
 					yTimeB[iIm] = f2_hi(y);
 				}
@@ -297,33 +352,51 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 #endif
 		// ---- one sweep over the ring: slot j ahead of the head gets, in the reference's order,
 		//      block A's sample j-addOff, the emission if j < gap, then block B's sample (relative to the new head)
-		auto contrib = [&](int i, bool second) -> float { return fmul((second ? yTimeB : yTimeA)[i], __ldg(x.window + i)); };
-		for (int j = tid; j < P; j += 256) {
-			int p = head + j;
-			if (p >= P) p -= P;
-			float pv = pend[p], wv = wp[p];
-			if (j >= addOff) { // block A (:397-399): i = j - addOff in [0, B)
-				const int i = j - addOff;
-				const float w = __ldg(x.window + i);
-				pv = fadd(pv, contrib(i, false));
-				wv = fadd(wv, fmul(fmul(w, w), fN));
-			}
-			if (hasB) {
-				int i = j - gap - addOff; // block B's sample for this slot, relative to the head after the emission
-				if (j < gap) { // emitted between the blocks (:408-414)
-					out[emitted + j] = fdiv(pv, wv);
+		//      (yTimeA / yTimeB already carry the synthesis window).  Two slots per iteration, loads first, branch-free.
+		{
+			const float *winProd = x.winProd;
+			auto slot = [&](int j, float &pv, float &wv, float &ya, float &wa, float &yb, float &wb, int &p, bool &okA, bool &okB) {
+				p = head + j;
+				if (p >= P) p -= P;
+				pv = pend[p];
+				wv = wp[p];
+				const int iA = j - addOff;
+				okA = j >= addOff; // block A (:397-399): i = j - addOff in [0, B)
+				ya = okA ? yTimeA[iA] : 0.f;
+				wa = okA ? __ldg(winProd + iA) : 0.f;
+				int iB = j - gap - addOff; // block B's sample for this slot, relative to the head after the emission
+				if (j < gap) iB += P;
+				okB = hasB && iB >= 0 && iB < B;
+				yb = okB ? yTimeB[iB] : 0.f;
+				wb = okB ? __ldg(winProd + iB) : 0.f;
+			};
+			auto finish = [&](int j, float pv, float wv, float ya, float wa, float yb, float wb, int p, bool okA, bool okB) {
+				if (okA) {
+					pv = fadd(pv, ya);
+					wv = fadd(wv, wa);
+				}
+				if (hasB && j < gap) { // emitted between the blocks (:408-414)
+					st_stream(out + emitted + j, fdiv(pv, wv));
 					pv = 0.f;
 					wv = B200S_ALMOST_ZERO;
-					i += P;
 				}
-				if (i >= 0 && i < B) {
-					const float w = __ldg(x.window + i);
-					pv = fadd(pv, contrib(i, true));
-					wv = fadd(wv, fmul(fmul(w, w), fN));
+				if (okB) {
+					pv = fadd(pv, yb);
+					wv = fadd(wv, wb);
 				}
+				pend[p] = pv;
+				wp[p] = wv;
+			};
+			for (int j = tid; j < P; j += 512) {
+				float pv0, wv0, ya0, wa0, yb0, wb0, pv1 = 0.f, wv1 = 0.f, ya1 = 0.f, wa1 = 0.f, yb1 = 0.f, wb1 = 0.f;
+				int p0, p1 = 0;
+				bool a0, b0, a1 = false, b1 = false;
+				const bool two = j + 256 < P;
+				slot(j, pv0, wv0, ya0, wa0, yb0, wb0, p0, a0, b0);
+				if (two) slot(j + 256, pv1, wv1, ya1, wa1, yb1, wb1, p1, a1, b1);
+				finish(j, pv0, wv0, ya0, wa0, yb0, wb0, p0, a0, b0);
+				if (two) finish(j + 256, pv1, wv1, ya1, wa1, yb1, wb1, p1, a1, b1);
 			}
-			pend[p] = pv;
-			wp[p] = wv;
 		}
 		if (hasB) {
 			// gap <= P always here?  blocks trigger every H <= B <= P samples; larger gaps cannot occur inside a call

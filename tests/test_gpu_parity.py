@@ -225,13 +225,13 @@ def test_fast_div_sqrt_are_correctly_rounded(gpu):
 @pytest.mark.gpu
 @pytest.mark.parametrize("blocks_per_call", [7, 40])
 def test_chain_kernel_generations_agree_bit_exactly(gpu, blocks_per_call):
-    """The three direct chain kernels (scalar lane-per-block, lane-per-(block,channel) multi-warp, packed f32x2
-    stereo) implement the same arithmetic: on identical spectra their outputs must be identical bit for bit
+    """The direct chain kernels (scalar lane-per-block, lane-per-(block,channel) multi-warp, packed f32x2
+    stereo, packed with the decoupled skew) implement the same arithmetic: on identical spectra their outputs must be identical bit for bit
     (guards the packed kernel against compiler contraction of multiply-add pairs).  40 blocks per call also
     exercises the second group / the warp hand-off."""
     cfg, C, sr, ratio, kind = signals.CONFIGS["config2_stereo_0p8x"]
     outs = []
-    for gen in (1, 2, 3):
+    for gen in (1, 2, 3, 4):
         e = gpu(5)
         cfg(e)
         e.set_tuning(0, gen)
@@ -241,6 +241,7 @@ def test_chain_kernel_generations_agree_bit_exactly(gpu, blocks_per_call):
         outs.append(signals.run_batch(e, x, ratio, blocks_per_call * H))
     assert np.array_equal(outs[0], outs[1]), "gen 2 differs: max %g" % np.abs(outs[0] - outs[1]).max()
     assert np.array_equal(outs[0], outs[2]), "gen 3 differs: max %g" % np.abs(outs[0] - outs[2]).max()
+    assert np.array_equal(outs[0], outs[3]), "gen 4 differs: max %g" % np.abs(outs[0] - outs[3]).max()
 
 
 @pytest.mark.gpu
