@@ -21,6 +21,70 @@ namespace b200s {
 // behind its own 8 while the next 8 are in flight (8 + 8 + CH4_FAR + 2 <= CH3_RING); beyond it: global gathers
 #define CH4_FAR (CH3_RING - 2 * CHAIN_CH - 3)
 
+// ---- FAST arithmetic (default on the GPU; b200s_set_tuning key 3 selects the exact mode) ------------------------
+// The exact mode reproduces the reference compiled WITHOUT floating-point contraction, operation by operation
+// (separate multiplies and adds, IEEE division and square root): about 40 % of the instructions of a step and most of
+// its dependent latency exist only for that.  The fast mode computes the same expressions the way an optimising build
+// of the reference does -- the reference's own shipped binary is built with -O3 -ffast-math
+// (web/emscripten/compile.sh:50): multiply-adds fused, the phase sum re-associated so that the term that closes the
+// recurrence is added last, a / b as a * rcp(b), phase * sqrt(energy / |phase|^2) as phase * (sqrt(energy) *
+// rsqrt(|phase|^2)) on the SFU approximations (1-2 ulp).  Results agree with the exact mode to float rounding per
+// operation; both are tested against the oracle to the north-star tolerance (tests/test_gpu_parity.py).
+#ifdef B200S_EMU
+__device__ __forceinline__ f2 neg2(f2 a) { return f2{-a.a, -a.b}; }
+__device__ __forceinline__ float rcp_fast(float b) { return 1.0f / b; }
+__device__ __forceinline__ float rsqrt_fast(float b) { return 1.0f / std::sqrt(b); }
+__device__ __forceinline__ float sqrt_fast(float b) { return std::sqrt(b); }
+__device__ __forceinline__ float ffma(float a, float b, float c) { return std::fma(a, b, c); }
+#else
+__device__ __forceinline__ float rcp_fast(float b) {
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+	return r;
+}
+__device__ __forceinline__ float rsqrt_fast(float b) {
+	float r;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+	return r;
+}
+__device__ __forceinline__ float sqrt_fast(float b) {
+	float r;
+	asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+	return r;
+}
+__device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#endif
+// a * b and a * conj(b), fused (4 packed instructions)
+__device__ __forceinline__ c2 fmul_c(c2 a, c2 b) {
+	return c2{fma2(a.re, b.re, neg2(mul2(a.im, b.im))), fma2(a.re, b.im, mul2(a.im, b.re))};
+}
+__device__ __forceinline__ c2 fmulc_c(c2 a, c2 b) {
+	return c2{fma2(a.re, b.re, mul2(a.im, b.im)), fma2(a.im, b.re, neg2(mul2(a.re, b.im)))};
+}
+// acc + a * b, acc + a * conj(b)
+__device__ __forceinline__ c2 fmul_acc(c2 acc, c2 a, c2 b) {
+	return c2{fma2(neg2(a.im), b.im, fma2(a.re, b.re, acc.re)), fma2(a.im, b.re, fma2(a.re, b.im, acc.im))};
+}
+__device__ __forceinline__ c2 fmulc_acc(c2 acc, c2 a, c2 b) {
+	return c2{fma2(a.im, b.im, fma2(a.re, b.re, acc.re)), fma2(neg2(a.re), b.im, fma2(a.im, b.re, acc.im))};
+}
+// a * (r.x + i r.y), r common to both channels
+__device__ __forceinline__ c2 fmul_s(c2 a, float2 r) {
+	return c2{fmas(a.im, -r.y, muls(a.re, r.x)), fmas(a.im, r.x, muls(a.re, r.y))};
+}
+__device__ __forceinline__ f2 fnorm2(c2 a) { return fma2(a.re, a.re, mul2(a.im, a.im)); }
+__device__ __forceinline__ c2 flerp2(c2 lo, c2 hi, float fr) { return c2{fmas(hi.re - lo.re, fr, lo.re), fmas(hi.im - lo.im, fr, lo.im)}; }
+__device__ __forceinline__ float2 fmul_f(float2 a, float2 b) { return make_float2(ffma(a.x, b.x, -a.y * b.y), ffma(a.x, b.y, a.y * b.x)); }
+__device__ __forceinline__ float2 fmulc_f(float2 a, float2 b) { return make_float2(ffma(a.x, b.x, a.y * b.y), ffma(a.y, b.x, -a.x * b.y)); }
+// Prediction::makeOutput (:596-603)
+__device__ __forceinline__ float2 make_output_fast(float2 phase, float energy, float2 input) {
+	const float pn = ffma(phase.x, phase.x, phase.y * phase.y);
+	const bool weak = pn <= B200S_NOISE_FLOOR;
+	const float pni = ffma(input.x, input.x, input.y * input.y) + B200S_NOISE_FLOOR;
+	const float g = sqrt_fast(energy) * rsqrt_fast(weak ? pni : pn);
+	return make_float2((weak ? input.x : phase.x) * g, (weak ? input.y : phase.y) * g);
+}
+
 // Tiles of k_chain_direct4: as Chain3Tiles ([bin][lane] tiles, conflict-free for the per-step reads and for the
 // quarter-warp fill), without the output-row table (Band::output rows of consecutive blocks are equidistant).
 // (Measured dead end, profiles/r01_v13: lane-private rows filled with cp.async.bulk -- UBLKCP takes uniform operands,
@@ -33,7 +97,7 @@ struct Chain4Tiles {
 	const float4 *rowIn[32], *rowPv[32];
 };
 
-template <int LT>
+template <int LT, bool FAST>
 __global__ void __launch_bounds__(32) k_chain_direct4(Ctx x) {
 	const Cfg &g = x.cfg;
 	const int K = g.K;
@@ -241,13 +305,113 @@ __global__ void __launch_bounds__(32) k_chain_direct4(Ctx x) {
 				t1P = t1N;
 				U.pvy[cb][i][lane] = make_float4(f2_lo(oc.re), f2_hi(oc.re), f2_lo(oc.im), f2_hi(oc.im));
 			};
+			// FAST arithmetic (see the top of the file): same data flow, fused operations, re-associated phase sum
+			auto step_fast = [&](const int i, auto farTag, auto intTag) {
+				constexpr bool FAR = decltype(farTag)::value, INTERIOR = decltype(intTag)::value;
+				const int q = k0 + i - G * lane;
+				const int b = q - LT - 1;
+				const bool qIn = INTERIOR || (active && (unsigned)q < (unsigned)K);
+				const float i2 = fsub((float)q, longTf);
+				const int l2 = (int)floorf(i2);
+				const float f2s = fsub(i2, (float)l2);
+				const float i1 = fsub((float)(b + 1), tf);
+				const int l1 = (int)floorf(i1);
+				const float f1s = fsub(i1, (float)l1);
+				c2 ro;
+				f2 re;
+				{
+					const float a0 = __shfl_up_sync(0xffffffffu, f2_lo(lastFinal.re), 1), a1 = __shfl_up_sync(0xffffffffu, f2_hi(lastFinal.re), 1);
+					const float b0 = __shfl_up_sync(0xffffffffu, f2_lo(lastFinal.im), 1), b1 = __shfl_up_sync(0xffffffffu, f2_hi(lastFinal.im), 1);
+					const float e0 = __shfl_up_sync(0xffffffffu, f2_lo(lastE), 1), e1 = __shfl_up_sync(0xffffffffu, f2_hi(lastE), 1);
+					const float4 p0 = U.p0Out[cb][i];
+					const float2 p0e = U.p0E[cb][i];
+					const bool first = lane == 0;
+					ro = c2{f2_make(first ? p0.x : a0, first ? p0.z : a1), f2_make(first ? p0.y : b0, first ? p0.w : b1)};
+					re = f2_make(first ? p0e.x : e0, first ? p0e.y : e1);
+				}
+				const c2 inq = ld_c2s(&U.in[q & (CH3_RING - 1)][lane]);
+				c2 pv = ld_c2s(&U.pvy[cb][i][lane]);
+				c2 lo2, hi2, lo1, hi1;
+				if constexpr (!FAR) {
+					lo2 = sel_c2(INTERIOR || l2 >= 0, ld_c2s(&U.in[l2 & (CH3_RING - 1)][lane]));
+					hi2 = sel_c2(INTERIOR || l2 >= -1, ld_c2s(&U.in[(l2 + 1) & (CH3_RING - 1)][lane]));
+					lo1 = sel_c2(INTERIOR || l1 >= 0, ld_c2s(&U.in[l1 & (CH3_RING - 1)][lane]));
+					hi1 = sel_c2(INTERIOR || l1 >= -1, ld_c2s(&U.in[(l1 + 1) & (CH3_RING - 1)][lane]));
+				} else {
+					lo2 = (l2 < 0 || l2 >= K) ? zc : ld_c2s(myIn + l2);
+					hi2 = (l2 + 1 < 0 || l2 + 1 >= K) ? zc : ld_c2s(myIn + l2 + 1);
+					lo1 = (l1 < 0 || l1 >= K) ? zc : ld_c2s(myIn + l1);
+					hi1 = (l1 + 1 < 0 || l1 + 1 >= K) ? zc : ld_c2s(myIn + l1 + 1);
+				}
+				pv = fmul_s(pv, rotq); // :653-654
+				ro = fmul_s(ro, rotq);
+				const f2 e = fnorm2(inq);                      // :679
+				const c2 ph0 = fmul_c(ro, fmulc_c(inq, pv));     // :714-715
+				const f2 den = f2_make(fmaxf(f2_lo(re), f2_lo(e)), fmaxf(f2_hi(re), f2_hi(e))) + f2_make(B200S_NOISE_FLOOR, B200S_NOISE_FLOOR);
+				const f2 rden = f2_make(rcp_fast(f2_lo(den)), rcp_fast(f2_hi(den)));
+				const c2 newPre = sel_c2(qIn, c2{mul2(ph0.re, rden), mul2(ph0.im, rden)}); // :716
+				const f2 newE = sel_f2(qIn, e);
+				const c2 newIn = sel_c2(qIn, inq);
+				const c2 newT2 = sel_c2(qIn, fmulc_c(inq, flerp2(lo2, hi2, f2s))); // long twist at q (:758)
+				const c2 t1N = fmulc_c(inF[1], flerp2(lo1, hi1, f1s));             // short twist at b+1 (:751,:771)
+				{
+					const float2 rn = xmul(rotq, rotS); // the table recurrence stays in the reference's own arithmetic
+					rotq = make_float2((INTERIOR || q >= 0) ? rn.x : rotq.x, (INTERIOR || q >= 0) ? rn.y : rotq.y);
+				}
+				const f2 eB = eF[0];
+				const c2 t2B = t2F[0], inB = inF[0];
+				const c2 preN = pre[1], preL = pre[LT], t2L = t2F[LT];
+#pragma unroll
+				for (int u = 0; u + 1 < NF; ++u) {
+					pre[u] = pre[u + 1];
+					eF[u] = eF[u + 1];
+					t2F[u] = t2F[u + 1];
+					inF[u] = inF[u + 1];
+				}
+				pre[NF - 1] = newPre;
+				eF[NF - 1] = newE;
+				t2F[NF - 1] = newT2;
+				inF[NF - 1] = newIn;
+				// ---- main prediction at bin b (:727-800); the terms that do not depend on the previous bin first
+				const bool m = f2_hi(eB) > f2_lo(eB);
+				const float maxE = m ? f2_hi(eB) : f2_lo(eB);
+				c2 ph2;
+				if constexpr (INTERIOR) {
+					ph2 = fmul_c(oh[LT - 1], t2B);        // :761
+					ph2 = fmulc_acc(ph2, preN, t1N);      // :774
+					ph2 = fmulc_acc(ph2, preL, t2L);      // :784
+					ph2 = fmul_acc(ph2, oh[0], t1P);      // :754
+				} else {
+					ph2 = sel_c2(b >= LT, fmul_c(oh[LT - 1], t2B));
+					ph2 = ph2 + sel_c2(b < K - 1, fmulc_c(preN, t1N));
+					ph2 = ph2 + sel_c2(b < K - LT, fmulc_c(preL, t2L));
+					ph2 = ph2 + sel_c2(b > 0, fmul_c(oh[0], t1P));
+				}
+				const float2 phase = pick(m, ph2), pinM = pick(m, inB);
+				const float2 outM = make_output_fast(phase, maxE, pinM); // :788
+				// the other channel is locked in phase (:791-799)
+				const float2 inO = pick(!m, inB);
+				const float eO = m ? f2_lo(eB) : f2_hi(eB);
+				const float2 outO = make_output_fast(fmul_f(outM, fmulc_f(inO, pinM)), eO, inO);
+				const c2 oc = c2{f2_make(m ? outO.x : outM.x, m ? outM.x : outO.x), f2_make(m ? outO.y : outM.y, m ? outM.y : outO.y)};
+#pragma unroll
+				for (int u = LT - 1; u > 0; --u) oh[u] = oh[u - 1];
+				oh[0] = oc;
+				lastFinal = oc;
+				lastE = eB;
+				t1P = t1N;
+				U.pvy[cb][i][lane] = make_float4(f2_lo(oc.re), f2_hi(oc.re), f2_lo(oc.im), f2_hi(oc.im));
+			};
 			// unrolled by 4 (for L = 4 the register FIFOs rotate by pure renaming) so that the hot loop stays in the
 			// instruction cache; branch-free inside
 			auto run_chunk = [&](auto farTag, auto intTag) {
 #pragma unroll 1
 				for (int h = 0; h < CHAIN_CH; h += 4) {
 #pragma unroll
-					for (int u = 0; u < 4; ++u) step(h + u, farTag, intTag);
+					for (int u = 0; u < 4; ++u) {
+						if constexpr (FAST) step_fast(h + u, farTag, intTag);
+						else step(h + u, farTag, intTag);
+					}
 				}
 			};
 			if (farAny) run_chunk(std::true_type{}, std::false_type{});

@@ -41,6 +41,7 @@ struct b200s_engine {
 	cudaStream_t subStream[kMaxSub] = {0, 0, 0, 0, 0, 0, 0, 0};
 	cudaEvent_t evBegin = 0, evSubDone[kMaxSub] = {0, 0, 0, 0, 0, 0, 0, 0};
 	int chainV = 0, fftV1 = 0; // b200s_set_tuning overrides (0 = default)
+	int exactMath = 0;         // b200s_set_tuning key 3: 1 = the phase chain in the reference's unfused IEEE arithmetic
 	int nHostParts = 8; // host-buffer API: stream groups whose H2D copy / kernels / D2H copy are pipelined
 	cudaEvent_t evStart = 0, evStop = 0;
 	long long launches = 0;
@@ -243,17 +244,21 @@ static int chain_version(const Cfg &g, int override, int forceFftV1) {
 	if (want >= 3 && !(g.C == 2 && use_pair_fft(g, forceFftV1))) want = 2;
 	return want;
 }
-static ChainKernel chain3_kernel(const Cfg &g, int v) {
-	if (v == 4) switch (g.L) {
-		case 1: return k_chain_direct4<1>;
-		case 2: return k_chain_direct4<2>;
-		case 3: return k_chain_direct4<3>;
-		case 4: return k_chain_direct4<4>;
-		case 5: return k_chain_direct4<5>;
-		case 6: return k_chain_direct4<6>;
-		case 7: return k_chain_direct4<7>;
-		default: return k_chain_direct4<8>;
-		}
+template <bool FAST>
+static ChainKernel chain4_kernel(int L) {
+	switch (L) {
+	case 1: return k_chain_direct4<1, FAST>;
+	case 2: return k_chain_direct4<2, FAST>;
+	case 3: return k_chain_direct4<3, FAST>;
+	case 4: return k_chain_direct4<4, FAST>;
+	case 5: return k_chain_direct4<5, FAST>;
+	case 6: return k_chain_direct4<6, FAST>;
+	case 7: return k_chain_direct4<7, FAST>;
+	default: return k_chain_direct4<8, FAST>;
+	}
+}
+static ChainKernel chain3_kernel(const Cfg &g, int v, bool fast) {
+	if (v == 4) return fast ? chain4_kernel<true>(g.L) : chain4_kernel<false>(g.L);
 	switch (g.L) {
 	case 1: return k_chain_direct3<1>;
 	case 2: return k_chain_direct3<2>;
@@ -544,7 +549,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 				// the spectra and k_prep is skipped; otherwise k_prep produces the coefficient arrays.
 				if (!plain) PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g), st, x));
 				if (plain && chainV >= 3) {
-					PROF(PK_CHAIN, B200S_LAUNCH(chain3_kernel(g, chainV), dim3(x.sCount), dim3(32), chainV == 4 ? smem_chain4(g.L) : sizeof(Chain3Tiles), st, x));
+					PROF(PK_CHAIN, B200S_LAUNCH(chain3_kernel(g, chainV, !e->exactMath), dim3(x.sCount), dim3(32), chainV == 4 ? smem_chain4(g.L) : sizeof(Chain3Tiles), st, x));
 				} else if (plain && chainV == 2) {
 					const int W = chain2_warps(g, nOut);
 					ChainKernel kc = chain2_kernel(g);
@@ -736,6 +741,7 @@ int b200s_set_tuning(b200s_engine *e, int key, int value) {
 	if (key == 0 && value >= 0 && value <= 4) e->chainV = value;
 	else if (key == 1 && (value == 0 || value == 1)) e->fftV1 = value;
 	else if (key == 2 && value >= 1) e->nHostParts = std::min(value, (int)b200s_engine::kMaxSub);
+	else if (key == 3 && (value == 0 || value == 1)) e->exactMath = value;
 	else {
 		e->err = "b200s_set_tuning: unknown key or value";
 		return B200S_EINVAL;

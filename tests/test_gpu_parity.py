@@ -235,6 +235,7 @@ def test_chain_kernel_generations_agree_bit_exactly(gpu, blocks_per_call):
         e = gpu(5)
         cfg(e)
         e.set_tuning(0, gen)
+        e.set_tuning(3, 1)  # exact arithmetic: generation 4 defaults to the fast (fused) mode
         H = e.intervalSamples()
         n_out = 3 * blocks_per_call * H
         x = signals.batch(kind, 5, C, int(round(n_out / ratio)), sr)
@@ -242,6 +243,29 @@ def test_chain_kernel_generations_agree_bit_exactly(gpu, blocks_per_call):
     assert np.array_equal(outs[0], outs[1]), "gen 2 differs: max %g" % np.abs(outs[0] - outs[1]).max()
     assert np.array_equal(outs[0], outs[2]), "gen 3 differs: max %g" % np.abs(outs[0] - outs[2]).max()
     assert np.array_equal(outs[0], outs[3]), "gen 4 differs: max %g" % np.abs(outs[0] - outs[3]).max()
+
+
+@pytest.mark.gpu
+def test_fast_and_exact_chain_arithmetic_agree_over_a_short_horizon(gpu):
+    """Default (fast: fused multiply-add, SFU reciprocal / rsqrt) against exact (the reference's unfused IEEE order)
+    arithmetic of the stereo direct chain on the same spectra: float rounding apart over the first blocks (the
+    recurrence is chaotic beyond), same level throughout."""
+    cfg, C, sr, ratio, kind = signals.CONFIGS["config2_stereo_0p8x"]
+    outs = []
+    for exact in (1, 0):
+        e = gpu(4)
+        cfg(e)
+        e.set_tuning(3, exact)
+        H = e.intervalSamples()
+        n_out = 24 * H
+        x = signals.batch(kind, 4, C, int(round(n_out / ratio)), sr)
+        outs.append(signals.run_batch(e, x, ratio, 12 * H))
+    lat = e.outputLatency() + int(e.inputLatency() * ratio)
+    assert not np.array_equal(outs[0], outs[1])
+    head = slice(lat, lat + 8 * H)
+    assert rms(outs[0][..., head] - outs[1][..., head]) <= 1e-5
+    assert rms(outs[0] - outs[1]) <= 1e-3
+    assert abs(20 * np.log10(rms(outs[0]) / rms(outs[1]))) <= 0.1
 
 
 @pytest.mark.gpu
