@@ -32,7 +32,9 @@ __host__ __device__ __forceinline__ int stage_len(int B) { return (B + 8 + 3) & 
 #ifdef B200S_EMU
 __device__ __forceinline__ float2 ld_stream(const float2 *p) { return *p; }
 __device__ __forceinline__ void st_stream(float *p, float v) { *p = v; }
+__device__ __forceinline__ void st_stream4(float *p, float4 v) { *(float4 *)p = v; }
 #else
+__device__ __forceinline__ void st_stream4(float *p, float4 v) { __stcs((float4 *)p, v); }
 __device__ __forceinline__ float2 ld_stream(const float2 *p) {
 	float2 v;
 	asm volatile("ld.global.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
@@ -269,7 +271,24 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 	__syncthreads();
 	int head = 0, emitted = 0;
 	// emit n samples from the ring head, zero them behind (:408-414)
+	// VECTOR form of the ring loops: when the ring head, the counts and the output row are multiples of four floats
+	// (the presets at 48 kHz with chunks that are multiples of four), four consecutive ring slots are one 16-byte
+	// shared-memory access each and never straddle the wrap; element for element the same operations in the same order.
+	const bool ioVec = ((uintptr_t)out & 15) == 0 && ((P | B | addOff) & 3) == 0;
 	auto emit = [&](int n) {
+		if (ioVec && ((head | n | emitted) & 3) == 0 && n <= P) {
+			for (int i = 4 * tid; i < n; i += 1024) {
+				int p = head + i;
+				if (p >= P) p -= P;
+				const float4 a = *(float4 *)(pend + p), w = *(float4 *)(wp + p);
+				st_stream4(out + emitted + i, make_float4(fdiv(a.x, w.x), fdiv(a.y, w.y), fdiv(a.z, w.z), fdiv(a.w, w.w)));
+				*(float4 *)(pend + p) = make_float4(0.f, 0.f, 0.f, 0.f);
+				*(float4 *)(wp + p) = make_float4(B200S_ALMOST_ZERO, B200S_ALMOST_ZERO, B200S_ALMOST_ZERO, B200S_ALMOST_ZERO);
+			}
+			head = (head + n) % P;
+			emitted += n;
+			return;
+		}
 		for (int i = tid; i < n; i += 256) {
 			float v = 0.f;
 			if (i < P) {
@@ -353,7 +372,36 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 		// ---- one sweep over the ring: slot j ahead of the head gets, in the reference's order,
 		//      block A's sample j-addOff, the emission if j < gap, then block B's sample (relative to the new head)
 		//      (yTimeA / yTimeB already carry the synthesis window).  Two slots per iteration, loads first, branch-free.
-		{
+		if (ioVec && ((head | gap | emitted) & 3) == 0) {
+			const float *winProd = x.winProd;
+			auto add4 = [](float4 a, float4 b) { return make_float4(fadd(a.x, b.x), fadd(a.y, b.y), fadd(a.z, b.z), fadd(a.w, b.w)); };
+#pragma unroll 2
+			for (int j = 4 * tid; j < P; j += 1024) {
+				int p = head + j;
+				if (p >= P) p -= P;
+				float4 pv = *(float4 *)(pend + p), wv = *(float4 *)(wp + p);
+				if (j >= addOff) { // block A (:397-399): i = j - addOff in [0, B)
+					const int iA = j - addOff;
+					pv = add4(pv, *(const float4 *)(yTimeA + iA));
+					wv = add4(wv, __ldg((const float4 *)(winProd + iA)));
+				}
+				if (hasB) {
+					int iB = j - gap - addOff; // block B's samples for these slots, relative to the head after the emission
+					if (j < gap) { // emitted between the blocks (:408-414)
+						st_stream4(out + emitted + j, make_float4(fdiv(pv.x, wv.x), fdiv(pv.y, wv.y), fdiv(pv.z, wv.z), fdiv(pv.w, wv.w)));
+						pv = make_float4(0.f, 0.f, 0.f, 0.f);
+						wv = make_float4(B200S_ALMOST_ZERO, B200S_ALMOST_ZERO, B200S_ALMOST_ZERO, B200S_ALMOST_ZERO);
+						iB += P;
+					}
+					if (iB >= 0 && iB < B) {
+						pv = add4(pv, *(const float4 *)(yTimeB + iB));
+						wv = add4(wv, __ldg((const float4 *)(winProd + iB)));
+					}
+				}
+				*(float4 *)(pend + p) = pv;
+				*(float4 *)(wp + p) = wv;
+			}
+		} else {
 			const float *winProd = x.winProd;
 			auto slot = [&](int j, float &pv, float &wv, float &ya, float &wa, float &yb, float &wb, int &p, bool &okA, bool &okB) {
 				p = head + j;
