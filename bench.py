@@ -328,7 +328,14 @@ def main():
     algo_bytes_step = ALGO_BYTES_PER_BLOCK_CHANNEL * args.batch * CHANNELS * BLOCKS_PER_STEP
     ms_step_dev = ms / args.steps
     achieved = algo_bytes_step / (ms_step_dev * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # measured DRAM traffic of the three large kernels for this workload (ncu --set full, committed under profiles/);
+    # only meaningful for the default configuration and batch
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if args.config == 2 and args.batch == BATCH_PER_GPU and os.path.exists(tpath):
+        traffic = float(json.load(open(tpath))["total_bytes_per_step"])
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/r01_traffic.json: dram read+write bytes per step of analyse+chain+synth (ncu --set full); algorithmic bytes per step: %d" % algo_bytes_step,
                 "peak_source": peak_src,
                 "scope": "whole process() launch sequence (the path is not yet one fused kernel): "
                          "%d algorithmic bytes per block-channel (SURVEY.md 8(d)) x %d block-channels per step / device time per step"

@@ -65,15 +65,24 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 	};
 	// item -> jobs; false when the stream has fewer pairs than slots
 	// (the three loads are independent of each other: the job slots exist even when the stream has fewer jobs)
-	auto fetch = [&](long long it, Item &m) -> bool {
+	// fetch_raw only issues the loads (m.hasB temporarily holds the stream's job count); fetch_done turns them into
+	// an item.  Keeping the two apart lets the loads of the item after next fly for a whole iteration.
+	auto fetch_raw = [&](long long it, Item &m) {
 		m.s = x.sBase + (int)(it / PJ);
-		const int p = (int)(it % PJ), nJ = x.call[m.s].nJobs;
-		const Job *jb = x.jobs + (size_t)m.s * 2 * g.C * x.maxFrames + 2 * p;
+		const Job *jb = x.jobs + (size_t)m.s * 2 * g.C * x.maxFrames + 2 * (int)(it % PJ);
+		m.hasB = x.call[m.s].nJobs;
 		m.a = jb[0];
 		m.b = jb[1];
+	};
+	auto fetch_done = [&](long long it, Item &m) -> bool {
+		const int p = (int)(it % PJ), nJ = m.hasB;
 		m.hasB = 2 * p + 1 < nJ;
 		if (!m.hasB) m.b = m.a;
 		return 2 * p < nJ;
+	};
+	auto fetch = [&](long long it, Item &m) -> bool {
+		fetch_raw(it, m);
+		return fetch_done(it, m);
 	};
 	auto next_valid = [&](long long it, Item &m) -> long long {
 		while (it < total && !fetch(it, m)) it += gridDim.x;
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 		if (nitem < total) { // start the next pair's input on its way while this FFT runs
 			stage_job(stA, nxt.s, nxt.a, 0, 256);
 			stage_job(stB, nxt.s, nxt.b, 32, 256);
-			if (cand < total) ok2 = fetch(cand, n2); // descriptor of the item after next: loads in flight until the end of the iteration
+			if (cand < total) fetch_raw(cand, n2); // descriptor of the item after next: loads in flight until the end of the iteration
 		}
 		pair_dit_stage_b<KT>(buf, tw, tid);
 		__syncthreads();
@@ -232,6 +241,7 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 		item = nitem;
 		cur = nxt;
 		if (nitem < total) {
+			if (cand < total) ok2 = fetch_done(cand, n2);
 			if (cand < total && !ok2) cand = next_valid(cand + gridDim.x, n2); // rare: a stream with fewer pairs than slots
 			nitem = cand < total ? cand : total;
 			nxt = n2;
