@@ -52,7 +52,7 @@ int b200s_synchronize(b200s_engine *e);
 int b200s_set_sub_batches(b200s_engine *e, int n);
 /* Implementation selectors for A/B measurement and cross-checking (results are identical by contract):
  *   key 0: direct chain kernel generation (1..4; 0 = default)   key 1: FFT kernels (1 = scalar Stockham, 0 = default paired)
- *   key 2: stream groups of the host-buffer pipeline in b200s_process (1..8)
+ *   key 2: stream groups of the host-buffer pipeline in b200s_process (1..16)
  *   key 3: arithmetic of the stereo direct phase chain: 0 = fast (default: fused multiply-adds, SFU reciprocal / square
  *          root, as an optimising build of the reference), 1 = exact (the reference's unfused IEEE operation order;
  *          bit-identical to the CPU oracle when the FFT is substituted -- used by the tests) */

@@ -36,10 +36,10 @@ struct b200s_engine {
 	cudaStream_t stream = 0;
 	bool ownStream = false;
 	// sub-batch pipeline: process() splits the batch over these prioritised streams (see process_impl)
-	static const int kMaxSub = 8;
+	static const int kMaxSub = 16;
 	int nSub = 1, maxSub = 1;
-	cudaStream_t subStream[kMaxSub] = {0, 0, 0, 0, 0, 0, 0, 0};
-	cudaEvent_t evBegin = 0, evSubDone[kMaxSub] = {0, 0, 0, 0, 0, 0, 0, 0};
+	cudaStream_t subStream[kMaxSub] = {};
+	cudaEvent_t evBegin = 0, evSubDone[kMaxSub] = {};
 	int chainV = 0, fftV1 = 0; // b200s_set_tuning overrides (0 = default)
 	int exactMath = 0;         // b200s_set_tuning key 3: 1 = the phase chain in the reference's unfused IEEE arithmetic
 	int nHostParts = 8; // host-buffer API: stream groups whose H2D copy / kernels / D2H copy are pipelined
@@ -258,7 +258,6 @@ static ChainKernel chain4_kernel(int L) {
 	}
 }
 static ChainKernel chain3_kernel(const Cfg &g, int v, bool fast) {
-	if (v == 4 && fast && g.L == 4 && getenv("B200S_CHAIN_UNR8")) return k_chain_direct4<4, true, 8>; // A/B experiment
 	if (v == 4) return fast ? chain4_kernel<true>(g.L) : chain4_kernel<false>(g.L);
 	switch (g.L) {
 	case 1: return k_chain_direct3<1>;
@@ -454,17 +453,6 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	if (use_pair_fft(g)) {
 		CK(cudaFuncSetAttribute(analyse2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_analyse2(g)));
 		CK(cudaFuncSetAttribute(synth2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_synth2(g)));
-		// one shared-memory carve-out for every kernel of the sequence: CTAs of kernels that prefer different carve-outs
-		// cannot be resident on an SM together (the SM has to drain to reconfigure), which serialises sub-batches
-		if (getenv("B200S_CARVEOUT")) {
-			const int co = atoi(getenv("B200S_CARVEOUT"));
-			CK(cudaFuncSetAttribute(analyse2_kernel(g), cudaFuncAttributePreferredSharedMemoryCarveout, co));
-			CK(cudaFuncSetAttribute(synth2_kernel(g), cudaFuncAttributePreferredSharedMemoryCarveout, co));
-			CK(cudaFuncSetAttribute(chain3_kernel(g, 4, true), cudaFuncAttributePreferredSharedMemoryCarveout, co));
-			CK(cudaFuncSetAttribute(chain3_kernel(g, 4, false), cudaFuncAttributePreferredSharedMemoryCarveout, co));
-			CK(cudaFuncSetAttribute(k_plan, cudaFuncAttributePreferredSharedMemoryCarveout, co));
-			CK(cudaFuncSetAttribute(k_commit, cudaFuncAttributePreferredSharedMemoryCarveout, co));
-		}
 	}
 	{
 		int n = 0;
