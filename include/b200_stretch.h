@@ -52,7 +52,7 @@ int b200s_synchronize(b200s_engine *e);
 int b200s_set_sub_batches(b200s_engine *e, int n);
 /* Implementation selectors for A/B measurement and cross-checking (results are identical by contract):
  *   key 0: direct chain kernel generation (1..4; 0 = default)   key 1: FFT kernels (1 = scalar Stockham, 0 = default paired)
- *   key 2: stream groups of the host-buffer pipeline in b200s_process (1..16)
+ *   key 2: stream groups of the host-buffer pipeline in b200s_process (1..16, default 12)
  *   key 3: arithmetic of the stereo direct phase chain: 0 = fast (default: fused multiply-adds, SFU reciprocal / square
  *          root, as an optimising build of the reference), 1 = exact (the reference's unfused IEEE operation order;
  *          bit-identical to the CPU oracle when the FFT is substituted -- used by the tests) */
@@ -98,6 +98,12 @@ int b200s_set_freq_map_table(b200s_engine *e, const float *freq_in, const float 
 int b200s_seek(b200s_engine *e, const float *in, int input_samples, double playback_rate);
 int b200s_output_seek(b200s_engine *e, const float *in, int input_length);
 int b200s_process(b200s_engine *e, const float *in, int input_samples, float *out, int output_samples);
+/* As b200s_process(), but returns as soon as the copies and kernels are enqueued: consecutive calls pipeline (stream
+ * group g of call n+1 starts its host->device copy while other groups still finish call n), which is how a server
+ * that streams chunk after chunk keeps both PCIe directions and the GPU busy.  `in` must stay valid and `out` must not
+ * be read until b200s_synchronize() (or any synchronous call) returns; pinned host memory is needed for the copies to
+ * be asynchronous at all. */
+int b200s_process_async(b200s_engine *e, const float *in, int input_samples, float *out, int output_samples);
 int b200s_flush(b200s_engine *e, float *out, int output_samples, float playback_rate);
 int b200s_exact(b200s_engine *e, const float *in, int input_samples, float *out, int output_samples, int *ok);
 /* Device-buffer variants: pointers are device memory on the handle's GPU, same planar layout;

@@ -40,9 +40,10 @@ struct b200s_engine {
 	int nSub = 1, maxSub = 1;
 	cudaStream_t subStream[kMaxSub] = {};
 	cudaEvent_t evBegin = 0, evSubDone[kMaxSub] = {};
+	int chainedGroups = 0; // > 0: the last operation was a host-buffer process() over this many stream groups (see process_impl)
 	int chainV = 0, fftV1 = 0; // b200s_set_tuning overrides (0 = default)
 	int exactMath = 0;         // b200s_set_tuning key 3: 1 = the phase chain in the reference's unfused IEEE arithmetic
-	int nHostParts = 8; // host-buffer API: stream groups whose H2D copy / kernels / D2H copy are pipelined
+	int nHostParts = 12; // (measured, batch 1024 stereo: 2 -> 15.1, 4 -> 13.0, 8 -> 12.2, 12 -> 11.2, 16 -> 11.8 ms per step) host-buffer API: stream groups whose H2D copy / kernels / D2H copy are pipelined
 	cudaEvent_t evStart = 0, evStop = 0;
 	long long launches = 0;
 	std::string err;
@@ -280,6 +281,7 @@ static size_t smem_chain(const Cfg &g, bool direct) {
 }
 
 static int reset_impl(b200s_engine *e, bool full) {
+	e->chainedGroups = 0;
 	Ctx x = make_ctx(e);
 	B200S_LAUNCH(k_reset_stft, dim3(e->S), dim3(kThreads), 0, e->stream, x);
 	CKL();
@@ -521,15 +523,22 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	// (b200s_profile_begin) runs unsplit on the main stream so that the event pairs time one kernel each.
 	const bool hostIO = hIn || hOut;
 	const int wantSub = hostIO ? e->nHostParts : e->nSub;
-	const int nSub = (e->profiling || wantSub <= 1 || g.S < 64) ? 1 : std::min(wantSub, e->maxSub);
-	if (nSub > 1) CK(cudaEventRecord(e->evBegin, e->stream));
+	// (host-buffer pipeline: at least two streams per group; device-resident sub-batches: only for large batches)
+	const int nSub = (e->profiling || wantSub <= 1 || g.S < (hostIO ? 2 * wantSub : 64)) ? 1 : std::min(wantSub, e->maxSub);
+	// Consecutive host-buffer calls over the SAME stream groups need no join between them: every group's copies and
+	// kernels are ordered on the group's own stream and touch only that group's streams of the state, so group g of
+	// call n+1 may start its H2D copy while other groups still finish call n (b200s_process_async pipelines calls this
+	// way).  Anything else first joins: the main stream has waited for every group at the end of the previous call.
+	const bool chained = hostIO && nSub > 1 && e->chainedGroups == nSub;
+	e->chainedGroups = (hostIO && nSub > 1) ? nSub : 0;
+	if (nSub > 1 && !chained) CK(cudaEventRecord(e->evBegin, e->stream));
 	const bool plain = !(e->prm.mapN > 0 || e->prm.freqMultiplier != 1.0f) && e->prm.formantMultiplier == 1.0f;
 	const int chainV = chain_version(g, e->chainV, e->fftV1);
 	const bool pairFft = use_pair_fft(g, e->fftV1);
 	x.specIl = (plain && chainV >= 3) ? 1 : 0;
 	for (int sub = 0; sub < nSub; ++sub) {
 		cudaStream_t st = nSub > 1 ? e->subStream[sub] : e->stream;
-		if (nSub > 1) CK(cudaStreamWaitEvent(st, e->evBegin, 0));
+		if (nSub > 1 && !chained) CK(cudaStreamWaitEvent(st, e->evBegin, 0));
 		x.sBase = (int)((long long)g.S * sub / nSub);
 		x.sCount = (int)((long long)g.S * (sub + 1) / nSub) - x.sBase;
 		if (hIn && nIn > 0)
@@ -581,6 +590,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 
 static int seek_impl(b200s_engine *e, const float *dIn, int chanStride, long long streamStride, int n, double playbackRate) {
 	const Cfg &g = e->cfg;
+	e->chainedGroups = 0;
 	Ctx x = make_ctx(e);
 	x.in = dIn; x.nIn = n; x.inChanStride = chanStride; x.inStreamStride = streamStride;
 	float stf = (playbackRate * g.H > 1) ? float(1 / playbackRate) : float(g.H); // :164
@@ -591,6 +601,7 @@ static int seek_impl(b200s_engine *e, const float *dIn, int chanStride, long lon
 
 static int flush_impl(b200s_engine *e, float *dOut, int outChanStride, long long outStreamStride, int nOut, float playbackRate) {
 	const Cfg &g = e->cfg;
+	e->chainedGroups = 0;
 	int rc;
 	int outputBlock = std::max(0, nOut - g.H); // :439
 	if (outputBlock > 0) {
@@ -876,6 +887,18 @@ int b200s_process(b200s_engine *e, const float *in, int nIn, float *out, int nOu
 	if ((rc = process_impl(e, e->dIn, nIn, (long long)e->cfg.C * nIn, nIn, e->dOut, nOut, (long long)e->cfg.C * nOut, nOut, in, out))) return rc;
 	CK(cudaStreamSynchronize(e->stream));
 	return 0;
+}
+int b200s_process_async(b200s_engine *e, const float *in, int nIn, float *out, int nOut) {
+	NEED_CFG();
+	int rc;
+	if ((rc = check_formant_support(e))) return rc;
+	if ((size_t)e->cfg.S * e->cfg.C * std::max(nIn, 1) > e->inCap || (size_t)e->cfg.S * e->cfg.C * std::max(nOut, 1) > e->outCap || !e->dIn || !e->dOut) {
+		// growing the staging buffers would invalidate copies still in flight: drain first
+		CK(cudaStreamSynchronize(e->stream));
+	}
+	if ((rc = stage_in(e, nullptr, nIn))) return rc;
+	if ((rc = stage_out(e, nOut))) return rc;
+	return process_impl(e, e->dIn, nIn, (long long)e->cfg.C * nIn, nIn, e->dOut, nOut, (long long)e->cfg.C * nOut, nOut, in, out);
 }
 int b200s_flush(b200s_engine *e, float *out, int nOut, float rate) {
 	NEED_CFG();

@@ -185,6 +185,30 @@ def test_api_sequence_bit_exact_vs_oracle(emu_libs, oracle_port):
     assert np.array_equal(ref, got), "max diff %g" % np.abs(ref - got).max()
 
 
+def test_async_host_calls_equal_blocking_calls(emu_libs):
+    """b200s_process_async (pipelined host-buffer calls over chained stream groups) gives what blocking calls give."""
+    import ctypes
+
+    x = signals.batch("harmonic", 4, 1, 1024, 48000)
+    outs = []
+    for use_async in (False, True):
+        g = _emu(emu_libs["float"], 4)
+        g.set_tuning(2, 2)  # two stream groups of two streams
+        g.configure(1, 256, 64)
+        g.setTransposeSemitones(3, 0)
+        ys = [np.zeros((4, 1, 256), np.float32) for _ in range(4)]
+        for k in range(4):
+            xi = np.ascontiguousarray(x[:, :, 256 * k:256 * (k + 1)])
+            if use_async:
+                g.process_host_ptr_async(xi.ctypes.data, 256, ys[k].ctypes.data, 256)
+                keep = xi  # noqa: F841  (the emulator copies synchronously; on a GPU the buffer must outlive the call)
+            else:
+                g.process_host_ptr(xi.ctypes.data, 256, ys[k].ctypes.data, 256)
+        g.synchronize()
+        outs.append(np.concatenate(ys, axis=2))
+    assert np.array_equal(outs[0], outs[1])
+
+
 def test_streams_are_independent_and_chunking_is_invariant(emu_libs):
     """A stream's output does not depend on its neighbours in the batch nor on the call chunking."""
     x = signals.batch("harmonic", 3, 1, 3000, 48000)
