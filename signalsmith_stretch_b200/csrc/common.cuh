@@ -111,6 +111,7 @@ struct Ctx {
 	float *pend, *pendWp;
 	float2 *stIn, *stPrev, *stOut;
 	float *stPredE;
+	float *stPitch; // [S][2] freqEstimateWeighted, freqEstimateWeight (:927-928): automatic pitch estimate of the formant envelope
 	// stereo direct path: spectra are channel-interleaved float4 {re0, re1, im0, im1} per bin (chain_direct3.cuh);
 	// stIl [S][2][K] holds such copies of stIn / stPrev, made by k_plan at the start of the call
 	float4 *stIl;
@@ -124,6 +125,7 @@ struct Ctx {
 	int inAligned; // input / history rows allow 16-byte cp.async (pointer, strides and lengths multiples of 4 floats)
 	float2 *spec, *Y, *cPI, *cFT, *cT1, *cT2;
 	float *cE;
+	float *cPitch; // [S][maxFrames] freqEstimate of every block when formantBaseFreq <= 0 (k_pitch)
 	// sub-batch of streams this launch covers (the batch is processed as a few sub-batches on
 	// prioritised CUDA streams so that different kernels of the sequence overlap on the SMs)
 	int sBase, sCount;

@@ -74,6 +74,7 @@ struct b200s_engine {
 	int numSMs = 148;
 	float2 *dSpec = 0, *dY = 0, *dPI = 0, *dFT = 0, *dT1 = 0, *dT2 = 0;
 	float *dE = 0;
+	float *dStPitch = 0, *dPitch = 0;
 	// staging for the host-buffer API and for flush/outputSeek
 	float *dIn = 0, *dOut = 0, *dZero = 0, *dTmp = 0;
 	size_t inCap = 0, outCap = 0, zeroCap = 0, tmpCap = 0;
@@ -118,7 +119,7 @@ static void free_all(b200s_engine *e) {
 	dfree(e->dWindow); dfree(e->dWinProd); dfree(e->dWpReset); dfree(e->dRot); dfree(e->dTwiddle); dfree(e->dPretw); dfree(e->dAnaTab);
 	dfree(e->dSched); dfree(e->dHist[0]); dfree(e->dHist[1]); dfree(e->dPend); dfree(e->dPendWp);
 	dfree(e->dStIn); dfree(e->dStPrev); dfree(e->dStOut); dfree(e->dStPredE); dfree(e->dStIl);
-	dfree(e->dFrames); dfree(e->dCall); dfree(e->dJobs); dfree(e->dSpec); dfree(e->dY); dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dE);
+	dfree(e->dFrames); dfree(e->dCall); dfree(e->dJobs); dfree(e->dSpec); dfree(e->dY); dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dE); dfree(e->dStPitch); dfree(e->dPitch);
 	dfree(e->dIn); dfree(e->dOut); dfree(e->dZero); dfree(e->dTmp);
 	e->maxFrames = 0;
 	e->inCap = e->outCap = e->zeroCap = e->tmpCap = 0;
@@ -142,7 +143,7 @@ static Ctx make_ctx(b200s_engine *e) {
 	x.maxFrames = e->maxFrames;
 	x.sBase = 0; x.sCount = e->S;
 	x.frames = e->dFrames; x.call = e->dCall; x.jobs = e->dJobs;
-	x.spec = e->dSpec; x.Y = e->dY; x.cPI = e->dPI; x.cFT = e->dFT; x.cT1 = e->dT1; x.cT2 = e->dT2; x.cE = e->dE;
+	x.spec = e->dSpec; x.Y = e->dY; x.cPI = e->dPI; x.cFT = e->dFT; x.cT1 = e->dT1; x.cT2 = e->dT2; x.cE = e->dE; x.stPitch = e->dStPitch; x.cPitch = e->dPitch;
 	return x;
 }
 
@@ -430,6 +431,8 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	if ((rc = dalloc(e, &e->dStIl, g.C == 2 ? (size_t)g.S * 2 * g.K : 1))) return rc;
 	if ((rc = dalloc(e, &e->dCall, g.S))) return rc;
 	CK(cudaMemset(e->dStPredE, 0, sizeof(float) * SC * g.K));
+	if ((rc = dalloc(e, &e->dStPitch, (size_t)g.S * 2))) return rc;
+	CK(cudaMemset(e->dStPitch, 0, sizeof(float) * (size_t)g.S * 2));
 	CK(cudaMemset(e->dHist[1], 0, sizeof(float) * SC * g.histLen));
 	{
 		std::vector<Sched> sc(g.S);
@@ -483,6 +486,7 @@ static int ensure_scratch(b200s_engine *e, int nOut) {
 	if ((rc = dalloc(e, &e->dT1, n))) return rc;
 	if ((rc = dalloc(e, &e->dT2, n))) return rc;
 	if ((rc = dalloc(e, &e->dE, n))) return rc;
+	if ((rc = dalloc(e, &e->dPitch, (size_t)g.S * need))) return rc;
 	e->maxFrames = need;
 	return 0;
 }
@@ -533,6 +537,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	e->chainedGroups = (hostIO && nSub > 1) ? nSub : 0;
 	if (nSub > 1 && !chained) CK(cudaEventRecord(e->evBegin, e->stream));
 	const bool plain = !(e->prm.mapN > 0 || e->prm.freqMultiplier != 1.0f) && e->prm.formantMultiplier == 1.0f;
+	const bool formantsOn = e->prm.formantMultiplier != 1.0f || (e->prm.formantCompensation && (e->prm.mapN > 0 || e->prm.freqMultiplier != 1.0f)); // :310
 	const int chainV = chain_version(g, e->chainV, e->fftV1);
 	const bool pairFft = use_pair_fft(g, e->fftV1);
 	x.specIl = (plain && chainV >= 3) ? 1 : 0;
@@ -556,6 +561,11 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 				}
 				// Pure time-stretch (no frequency map, no formants): the chain forms its terms directly from
 				// the spectra and k_prep is skipped; otherwise k_prep produces the coefficient arrays.
+				// formants with setFormantBase(0): the automatic pitch estimate of every block (serial over blocks) first
+				if (!plain && formantsOn && !(e->prm.formantBaseFreq > 0)) {
+					B200S_LAUNCH(k_pitch, dim3(x.sCount), dim3(kThreads), sizeof(float) * g.K, st, x);
+					CKL();
+				}
 				if (!plain) PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g), st, x));
 				if (plain && chainV >= 3) {
 					PROF(PK_CHAIN, B200S_LAUNCH(chain3_kernel(g, chainV, !e->exactMath), dim3(x.sCount), dim3(32), chainV == 4 ? smem_chain4(g.L) : sizeof(Chain3Tiles), st, x));
@@ -575,7 +585,8 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 				ChainKernel ks = synth_kernel(g);
 				PROF(PK_SYNTH, B200S_LAUNCH(ks, dim3(g.C, x.sCount), dim3(kThreads), smem_synth(g), st, x));
 			}
-			if (!pairFft) PROF(PK_COMMIT, B200S_LAUNCH(k_commit, dim3(x.sCount), dim3(kThreads), 0, st, x)); // (k_synth2 commits its own stream-channel)
+			// (measured: folding the commit into k_synth2's CTAs costs more there than the launch saves: 4.76 vs 4.68 ms)
+			PROF(PK_COMMIT, B200S_LAUNCH(k_commit, dim3(x.sCount), dim3(kThreads), 0, st, x));
 		}
 		if (hOut && nOut > 0)
 			CK(cudaMemcpyAsync(hOut + (size_t)x.sBase * g.C * nOut, dOut + (size_t)x.sBase * g.C * nOut, sizeof(float) * (size_t)x.sCount * g.C * nOut, cudaMemcpyDeviceToHost, st));
@@ -842,16 +853,7 @@ int b200s_set_freq_map_table(b200s_engine *e, const float *fin, const float *fou
 	return 0;
 }
 
-static int check_formant_support(b200s_engine *e) {
-	const Params &p = e->prm;
-	bool mapped = p.mapN > 0 || p.freqMultiplier != 1.0f;
-	bool formants = p.formantMultiplier != 1.0f || (p.formantCompensation && mapped);
-	if (formants && !(p.formantBaseFreq > 0)) {
-		e->err = "formant processing on the GPU path needs setFormantBase(f > 0); automatic pitch detection (setFormantBase(0)) is not implemented yet";
-		return B200S_EUNSUPPORTED;
-	}
-	return 0;
-}
+static int check_formant_support(b200s_engine *) { return 0; } // automatic pitch detection (setFormantBase(0)) runs on the GPU: k_pitch
 
 int b200s_seek_device(b200s_engine *e, const float *dIn, int n, double rate) {
 	NEED_CFG();

@@ -264,8 +264,6 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 	const int c = blockIdx.x, s = x.sBase + blockIdx.y, tid = threadIdx.x;
 	const Call cl = x.call[s];
 	float *out = x.out + (size_t)s * x.outStreamStride + (size_t)c * x.outChanStride;
-	// history append and state carry of this stream-channel (:418, :806-812): what k_commit does on the generic path
-	commit_channel(x, s, c, tid, 256);
 	if (cl.bypass) { // :252-267
 		const float *in = x.in + (size_t)s * x.inStreamStride + (size_t)c * x.inChanStride;
 		for (int i = tid; i < x.nOut; i += 256) out[i] = x.nIn > 0 ? in[i % x.nIn] : 0.f;

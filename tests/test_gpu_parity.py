@@ -91,6 +91,30 @@ def test_free_run_vs_oracle_batch(gpu, oracle_port, name):
         assert per.max() <= 1e-3 and rms(d) <= 1e-3, (per, rms(d))
 
 
+def test_automatic_formant_pitch_vs_oracle(gpu, oracle_port):
+    """setFormantBase(0): the per-block pitch estimate (estimateFrequency :929-966, k_pitch) and its smoothing state,
+    carried over calls -- stereo, +12 semitones with formant compensation, several calls per stream."""
+    def cfg(o):
+        o.presetDefault(2, 48000.0)
+        o.setTransposeSemitones(12, 0)
+        o.setFormantFactor(1, True)
+        o.setFormantBase(0)
+
+    S = 4
+    e = gpu(S)
+    cfg(e)
+    H, B = e.intervalSamples(), e.blockSamples()
+    n_out = 12 * H + B
+    x = signals.batch("harmonic", S, 2, n_out, 48000)
+    y = signals.run_batch(e, x, 1.0, 4 * H)  # four blocks per call: the estimate's state crosses calls
+    ref = _oracle_batch(oracle_port, cfg, x, 1.0, 4 * H)
+    lat = e.outputLatency() + e.inputLatency()
+    d = y - ref
+    per = np.array([rms(d[s][:, : lat + 8 * H]) for s in range(S)])
+    assert np.median(per) <= 1e-4, per
+    assert per.max() <= 1e-3 and rms(d) <= 1e-3, (per, rms(d))
+
+
 @pytest.mark.parametrize("name", [n for n in signals.CONFIGS if n != "identity"])
 def test_teacher_forced_block_by_block(gpu, oracle_port, name):
     """T1 of SURVEY.md section 8(c): before every call the oracle's complete signal state (history,

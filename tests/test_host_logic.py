@@ -87,6 +87,9 @@ SMALL = [
     ("split_400_160", lambda o: (o.configure(1, 400, 160, True), o.setTransposeSemitones(2, 0)), 1, 1.0, 500),
     ("formant_comp_stereo", lambda o: (o.configure(2, 512, 128), o.setTransposeSemitones(12, 0), o.setFormantFactor(1, True), o.setFormantBase(200 / 48000)), 2, 1.0, 640),
     ("formant_+3st_1.25x", lambda o: (o.configure(1, 512, 128), o.setTransposeSemitones(-3, 0.2), o.setFormantSemitones(3, False), o.setFormantBase(300 / 48000)), 1, 1.25, 640),
+    # setFormantBase(0): automatic pitch estimate per block (estimateFrequency :929-966, k_pitch), state carried over calls
+    ("formant_auto_pitch_stereo", lambda o: (o.configure(2, 512, 128), o.setTransposeSemitones(5, 0), o.setFormantFactor(1, True), o.setFormantBase(0)), 2, 1.0, 640),
+    ("formant_auto_pitch_+4st_0.8x", lambda o: (o.configure(1, 384, 96), o.setFormantSemitones(4, False), o.setFormantBase(0)), 1, 0.8, 500),
 ]
 
 
@@ -248,11 +251,8 @@ def test_unsupported_features_fail_loudly(emu_libs):
         g.process(np.zeros((1, 1, 10), np.float32), 10)  # not configured
     with pytest.raises(StretchError, match="channels"):
         g.configure(3, 512, 128)
-    g.configure(1, 512, 128)
-    g.setFormantSemitones(3)
-    g.setFormantBase(0)  # automatic pitch detection for formants: not on the GPU path yet
-    with pytest.raises(StretchError, match="setFormantBase"):
-        g.process(np.zeros((1, 1, 10), np.float32), 10)
+    with pytest.raises(StretchError, match="unknown key"):
+        g.set_tuning(99, 0)
 
 
 # ------------------------------------------------------------------ sharding, gloo world_size 2
