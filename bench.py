@@ -344,17 +344,21 @@ def main():
     achieved = algo_bytes_step / (ms_step_dev * 1e-3) / 1e9
     # measured DRAM traffic of the three large kernels for this workload (ncu --set full, committed under profiles/);
     # only meaningful for the default configuration and batch
-    traffic = None
+    traffic, kernel_dram = None, None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if args.config == 2 and args.batch == BATCH_PER_GPU and os.path.exists(tpath):
-        traffic = float(json.load(open(tpath))["total_bytes_per_step"])
+        tj = json.load(open(tpath))
+        traffic = float(tj["total_bytes_per_step"])
+        # measured DRAM bytes of each large kernel / its measured duration in THIS run: how close each one is to the HBM bound
+        kernel_dram = {k: {"dram_gbs": v / (kern[k] * 1e-3) / 1e9, "frac_of_peak": v / (kern[k] * 1e-3) / 1e9 / peak}
+                       for k, v in tj["dram_bytes_per_launch"].items() if kern.get(k, 0) > 0}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "profiles/r01_traffic.json: dram read+write bytes per step of analyse+chain+synth (ncu --set full); algorithmic bytes per step: %d" % algo_bytes_step,
                 "peak_source": peak_src,
                 "scope": "whole process() launch sequence (the path is not yet one fused kernel): "
                          "%d algorithmic bytes per block-channel (SURVEY.md 8(d)) x %d block-channels per step / device time per step"
                          % (ALGO_BYTES_PER_BLOCK_CHANNEL, args.batch * CHANNELS * BLOCKS_PER_STEP),
-                "kernel_ms_per_step": kern, "kernel_share": {k: v / ksum for k, v in kern.items()}, "dominant_kernel": dominant}
+                "kernel_ms_per_step": kern, "kernel_dram": kernel_dram, "kernel_share": {k: v / ksum for k, v in kern.items()}, "dominant_kernel": dominant}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
