@@ -319,6 +319,17 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 		// samples emitted between the two blocks; without a second block nothing is emitted inside the sweep
 		const int gap = hasB ? frames[f + 1].t - tA : 0;
 		const float2 *YA = x.Y + coef_off(x, s, f, c), *YB = x.Y + coef_off(x, s, hasB ? f + 1 : f, c);
+#ifndef B200S_EMU
+		// the spectra of the NEXT pair of blocks start their way from HBM to L2 now (two rows of 8*K bytes, one 128-byte
+		// line per thread and step), so that the loads at the top of the next iteration find them there
+		if (f + 2 < cl.nFrames) {
+			const char *nA = (const char *)(x.Y + coef_off(x, s, f + 2, c)), *nB = (const char *)(x.Y + coef_off(x, s, min(f + 3, cl.nFrames - 1), c));
+			for (int o2 = tid * 128; o2 < KT * 8; o2 += 256 * 128) {
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(nA + o2));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(nB + o2));
+			}
+		}
+#endif
 #ifndef B200S_EMU_EXACT_FFT
 		// ---- first inverse-FFT pass takes its inputs straight from HBM (in flight while the ring is being emitted):
 		//      Z'[k] = Y[2k] for k < K/2, conj(Y[2(K-1-k)+1]) otherwise; thread tid < M1 needs k = q*M1 + tid, q = 0..15

@@ -125,7 +125,7 @@ def test_long_calls_multi_warp_chain_bit_exact_vs_oracle(emu_libs, oracle_port, 
 PRESET_CALLS = [
     # preset sizes run on the paired-FFT kernels (stft2.cuh); with the oracle's FFT swapped in, their staging,
     # job pairing and fused overlap-add sweep must reproduce the oracle bit for bit
-    ("default_stereo_0.8x", lambda o: o.presetDefault(2, 48000.0), 2, 0.8, 16000, 5760),  # aligned 16-byte staging
+    ("default_stereo_0.8x", lambda o: o.presetDefault(2, 48000.0), 2, 0.8, 12800, 5760),  # aligned 16-byte staging, two calls
     ("default_mono_1.25x_odd", lambda o: o.presetDefault(1, 48000.0), 1, 1.25, 12000, 4999),  # unaligned chunks, odd block counts
     ("cheaper_mono_split", lambda o: o.presetCheaper(1, 48000.0), 1, 1.0, 14000, 6000),
 ]
