@@ -586,7 +586,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 				PROF(PK_SYNTH, B200S_LAUNCH(ks, dim3(g.C, x.sCount), dim3(kThreads), smem_synth(g), st, x));
 			}
 			// (measured: folding the commit into k_synth2's CTAs costs more there than the launch saves: 4.76 vs 4.68 ms)
-			PROF(PK_COMMIT, B200S_LAUNCH(k_commit, dim3(x.sCount), dim3(kThreads), 0, st, x));
+			PROF(PK_COMMIT, B200S_LAUNCH(k_commit, dim3(g.C, x.sCount), dim3(kThreads), 0, st, x));
 		}
 		if (hOut && nOut > 0)
 			CK(cudaMemcpyAsync(hOut + (size_t)x.sBase * g.C * nOut, dOut + (size_t)x.sBase * g.C * nOut, sizeof(float) * (size_t)x.sCount * g.C * nOut, cudaMemcpyDeviceToHost, st));
