@@ -168,7 +168,7 @@ static double bessel0(double x) {
 
 static const int kThreads = 256;
 static size_t smem_analyse(const Cfg &g) { return sizeof(float2) * 2 * fft_buf_len(g.K) + sizeof(float) * (g.B + 4); }
-static size_t smem_prep(const Cfg &g) { return sizeof(float) * (7 * (size_t)g.K + 8); }
+static size_t smem_prep(const Cfg &g, bool formants = true) { return sizeof(float) * ((formants ? 7 : 5) * (size_t)g.K + 8); }
 static size_t smem_synth(const Cfg &g) { return sizeof(float2) * 2 * fft_buf_len(g.K) + sizeof(float) * 2 * g.pendLen; }
 
 enum { PK_PLAN = 0, PK_ANALYSE, PK_PREP, PK_CHAIN, PK_SYNTH, PK_COMMIT, PK_COUNT };
@@ -566,7 +566,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 					B200S_LAUNCH(k_pitch, dim3(x.sCount), dim3(kThreads), sizeof(float) * g.K, st, x);
 					CKL();
 				}
-				if (!plain) PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g), st, x));
+				if (!plain) PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g, formantsOn), st, x));
 				if (plain && chainV >= 3) {
 					PROF(PK_CHAIN, B200S_LAUNCH(chain3_kernel(g, chainV, !e->exactMath), dim3(x.sCount), dim3(32), chainV == 4 ? smem_chain4(g.L) : sizeof(Chain3Tiles), st, x));
 				} else if (plain && chainV == 2) {

@@ -91,6 +91,28 @@ def test_free_run_vs_oracle_batch(gpu, oracle_port, name):
         assert per.max() <= 1e-3 and rms(d) <= 1e-3, (per, rms(d))
 
 
+@pytest.mark.parametrize("ratio", [1.5, 0.75])
+def test_stereo_preset_cheaper_plain_vs_oracle(gpu, oracle_port, ratio):
+    """presetCheaper stereo without transposition: K = 2560 = 16*16*10 paired FFT, L = 3 (odd lane skew) in the packed
+    stereo chain (fast arithmetic), split computation (ring of block + interval samples) in the vector overlap-add."""
+    def cfg(o):
+        o.presetCheaper(2, 48000.0)
+
+    S = 4
+    e = gpu(S)
+    cfg(e)
+    H, B = e.intervalSamples(), e.blockSamples()
+    n_out = 12 * H + B
+    x = signals.batch("harmonic", S, 2, int(round(n_out / ratio)), 48000)
+    y = signals.run_batch(e, x, ratio, 6 * H)
+    ref = _oracle_batch(oracle_port, cfg, x, ratio, 6 * H)
+    lat = e.outputLatency() + int(e.inputLatency() * ratio)
+    d = y - ref
+    per = np.array([rms(d[s][:, : lat + 8 * H]) for s in range(S)])
+    assert np.median(per) <= 1e-4, per
+    assert per.max() <= 1e-3 and rms(d) <= 1e-3, (per, rms(d))
+
+
 def test_automatic_formant_pitch_vs_oracle(gpu, oracle_port):
     """setFormantBase(0): the per-block pitch estimate (estimateFrequency :929-966, k_pitch) and its smoothing state,
     carried over calls -- stereo, +12 semitones with formant compensation, several calls per stream."""
