@@ -168,7 +168,7 @@ static double bessel0(double x) {
 
 static const int kThreads = 256;
 static size_t smem_analyse(const Cfg &g) { return sizeof(float2) * 2 * fft_buf_len(g.K) + sizeof(float) * (g.B + 4); }
-static size_t smem_prep(const Cfg &g, bool formants = true) { return sizeof(float) * ((formants ? 7 : 5) * (size_t)g.K + 8); }
+static size_t smem_prep(const Cfg &g, bool formants = true) { return sizeof(float) * ((formants ? 7 : 6) * (size_t)g.K + 8); }
 static size_t smem_synth(const Cfg &g) { return sizeof(float2) * 2 * fft_buf_len(g.K) + sizeof(float) * 2 * g.pendLen; }
 
 enum { PK_PLAN = 0, PK_ANALYSE, PK_PREP, PK_CHAIN, PK_SYNTH, PK_COMMIT, PK_COUNT };

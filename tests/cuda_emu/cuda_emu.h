@@ -79,7 +79,11 @@ static inline T shfl_from(T v, int srcLane) {
 
 template <typename F>
 static void launch(dim3 grid, dim3 block, size_t smemBytes, F fn) {
-	(void)smemBytes;
+	// canary behind the dynamic shared memory the launch asked for: a kernel that writes past its allocation (an
+	// "illegal memory access" on the GPU) is caught here
+	const size_t canaryBytes = std::min<size_t>(16384, sizeof(dyn_smem) - std::min(smemBytes, sizeof(dyn_smem)));
+	unsigned char *canary = (unsigned char *)dyn_smem + std::min(smemBytes, sizeof(dyn_smem));
+	memset(canary, 0xA5, canaryBytes);
 	const int T = (int)(block.x * block.y * block.z);
 	BlockCtx ctx;
 	pthread_barrier_init(&ctx.blockBar, nullptr, T);
@@ -106,6 +110,11 @@ static void launch(dim3 grid, dim3 block, size_t smemBytes, F fn) {
 		});
 	}
 	for (auto &t : th) t.join();
+	for (size_t i = 0; i < canaryBytes; ++i)
+		if (canary[i] != 0xA5) {
+			fprintf(stderr, "cuda_emu: a kernel wrote %zu bytes past its %zu bytes of dynamic shared memory\n", i + 1, smemBytes);
+			abort();
+		}
 	for (int w = 0; w < nw; ++w) pthread_barrier_destroy(&ctx.warpBar[w]);
 	pthread_barrier_destroy(&ctx.blockBar);
 	g_ctx = nullptr;
