@@ -47,8 +47,8 @@ int b200s_version(int *major, int *minor, int *patch); /* reference `version[3]`
 /* Use an existing CUDA stream (a cudaStream_t passed as void*) instead of the handle's own. */
 int b200s_set_stream(b200s_engine *e, void *cuda_stream);
 int b200s_synchronize(b200s_engine *e);
-/* process() can split the batch into up to 4 sub-batches on prioritised CUDA streams so that the
- * different kernels of its launch sequence overlap (default 1 = off). */
+/* Device-buffer process() can split the batch into sub-batches on prioritised CUDA streams (default 1 = off:
+ * measured slower on B200).  The host-buffer calls always pipeline stream groups (key 2 below). */
 int b200s_set_sub_batches(b200s_engine *e, int n);
 /* Implementation selectors for A/B measurement and cross-checking (results are identical by contract):
  *   key 0: direct chain kernel generation (1..4; 0 = default)   key 1: FFT kernels (1 = scalar Stockham, 0 = default paired)
