@@ -315,6 +315,35 @@ def test_fast_and_exact_chain_arithmetic_agree_over_a_short_horizon(gpu):
 
 
 @pytest.mark.gpu
+def test_async_pipelined_host_calls_equal_blocking_calls(gpu):
+    """b200s_process_async: consecutive host-buffer calls chained over the stream groups (no join between calls, the
+    copies of one call overlapping the kernels of its neighbours) give bit for bit what blocking calls give."""
+    import torch
+
+    cfg, C, sr, ratio, kind = signals.CONFIGS["config2_stereo_0p8x"]
+    S, calls = 48, 4
+    outs = []
+    for use_async in (False, True):
+        e = gpu(S)
+        cfg(e)
+        H = e.intervalSamples()
+        n_out = 6 * H
+        n_in = int(round(n_out / ratio))
+        x = signals.batch(kind, S, C, n_in * calls, sr)
+        xs = [torch.from_numpy(np.ascontiguousarray(x[:, :, k * n_in:(k + 1) * n_in])).pin_memory() for k in range(calls)]
+        ys = [torch.zeros((S, C, n_out), dtype=torch.float32).pin_memory() for _ in range(calls)]
+        for k in range(calls):
+            if use_async:
+                e.process_host_ptr_async(xs[k].data_ptr(), n_in, ys[k].data_ptr(), n_out)
+            else:
+                e.process_host_ptr(xs[k].data_ptr(), n_in, ys[k].data_ptr(), n_out)
+        e.synchronize()
+        outs.append(np.concatenate([y.numpy().copy() for y in ys], axis=2))
+    assert np.abs(outs[0]).max() > 0.01
+    assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.gpu
 def test_paired_fft_kernels_match_scalar_fft_kernels(gpu):
     """Paired in-place packed FFT kernels vs the first-generation scalar Stockham kernels: same transform,
     different rounding -- identity configuration agrees to float precision."""
