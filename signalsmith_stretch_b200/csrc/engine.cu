@@ -3,7 +3,9 @@
 // The host does no DSP: it sizes buffers, builds the constant tables once per configure() and
 // enqueues kernels on one CUDA stream.  Even the block scheduler runs on the device (k_plan), so
 // a process() call is a fixed, sync-free launch sequence:
-//     k_plan -> k_analyse -> k_prep -> k_chain -> k_synth -> k_commit
+//     k_plan -> k_analyse[2] -> [k_pitch] -> [k_prep] -> k_chain[_direct{,2,3,4}] -> k_synth[2] -> k_commit
+// (the presets run the paired-FFT kernels of stft2.cuh and, stereo without frequency map / formants, k_chain_direct4;
+//  k_prep only for mapped / formant configurations, k_pitch only with setFormantBase(0))
 // Reference for every step: /root/reference/signalsmith-stretch.h (cited per kernel in kernels.cuh).
 #include <algorithm>
 #include <cmath>
