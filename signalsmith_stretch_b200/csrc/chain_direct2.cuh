@@ -53,7 +53,7 @@ struct Chain2Sync {
 __device__ __forceinline__ int ld_volatile_shared(const int *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ void st_volatile_shared(int *p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 __device__ __forceinline__ void fence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-__device__ __forceinline__ void spin_pause() { sched_yield(); }
+__device__ __forceinline__ void spin_pause() { emu_yield(); } // the emulator's threads are cooperative fibers
 #else
 __device__ __forceinline__ int ld_volatile_shared(const int *p) { return *(volatile const int *)p; }
 __device__ __forceinline__ void st_volatile_shared(int *p, int v) { *(volatile int *)p = v; }

@@ -1,18 +1,19 @@
 // tests/cuda_emu/cuda_emu.h -- TEST INFRASTRUCTURE ONLY.
 //
-// A minimal "CUDA on CPU" shim: one OS thread per CUDA thread, one block at a time, barriers for
-// __syncthreads / warp shuffles.  It exists because the build container has no GPU: it lets the
+// A minimal "CUDA on CPU" shim: one cooperative fiber per CUDA thread, one block at a time, yielding barriers
+// for __syncthreads / warp shuffles.  It exists because the build container has no GPU: it lets the
 // `-m "not gpu"` tests execute the SAME kernel sources (signalsmith_stretch_b200/csrc/*.cu*)
 // and check their logic against the oracle before they ever reach a B200.  It is compiled only by
 // tests/cuda_emu/build.sh into tests/cuda_emu/_build/, is never shipped, and the product package
 // cannot load it (signalsmith_stretch_b200 only loads the nvcc-built library).  Not a fallback.
 #pragma once
-#include <pthread.h>
 #include <sched.h>
+#include <ucontext.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -53,28 +54,92 @@ template <typename T>
 static inline T __ldg(const T *p) { return *p; }
 
 namespace emu {
-struct BlockCtx {
-	pthread_barrier_t blockBar;
-	std::vector<pthread_barrier_t> warpBar;
-	std::vector<uint32_t> shfl; // one slot per thread
+// ---- cooperative fibers: every CUDA thread of the block is a ucontext fiber on ONE OS thread, scheduled round
+// robin; barriers and shuffles yield until everybody has arrived.  (The first version used one OS thread per CUDA
+// thread and pthread barriers: 256 threads on a handful of cores spent almost all their time in futex calls.)
+struct Fiber {
+	ucontext_t uc;
+	uint3 tIdx, bIdx;
+	bool done;
 };
-static BlockCtx *g_ctx = nullptr;
+struct Bar {
+	int count = 0, gen = 0, n = 0;
+};
+static std::vector<Fiber> g_f;
+static std::vector<char *> g_stacks;
+static const size_t kStack = 512 * 1024;
+static ucontext_t g_main;
+static int g_cur = 0, g_T = 0;
+static Bar g_blockBar;
+static std::vector<Bar> g_warpBar;
+static std::vector<uint32_t> g_shfl;
+static std::function<void()> g_fn;
+static dim3 g_grid;
 static thread_local int t_tid = 0;
 
-static inline void warp_barrier() { pthread_barrier_wait(&g_ctx->warpBar[t_tid >> 5]); }
+static inline void load(int i) {
+	g_cur = i;
+	t_tid = i;
+	threadIdx = g_f[i].tIdx;
+	blockIdx = g_f[i].bIdx;
+}
+// give the processor to the next fiber that has not finished
+static inline void yield() {
+	const int from = g_cur;
+	g_f[from].tIdx = threadIdx;
+	g_f[from].bIdx = blockIdx;
+	int nx = from;
+	do {
+		nx = nx + 1 == g_T ? 0 : nx + 1;
+	} while (g_f[nx].done && nx != from);
+	if (nx == from) return;
+	load(nx);
+	swapcontext(&g_f[from].uc, &g_f[nx].uc);
+}
+static inline void bar_wait(Bar &b) {
+	const int gen = b.gen;
+	if (++b.count == b.n) {
+		b.count = 0;
+		++b.gen;
+	} else {
+		while (b.gen == gen) yield();
+	}
+}
+static inline void warp_barrier() { bar_wait(g_warpBar[t_tid >> 5]); }
 template <typename T>
 static inline T shfl_from(T v, int srcLane) {
 	static_assert(sizeof(T) == 4, "32-bit shuffles only");
 	uint32_t bits;
 	memcpy(&bits, &v, 4);
-	g_ctx->shfl[t_tid] = bits;
+	g_shfl[t_tid] = bits;
 	warp_barrier();
 	int base = t_tid & ~31, n = std::min<int>(32, (int)blockDim.x - base);
-	uint32_t r = (srcLane >= 0 && srcLane < n) ? g_ctx->shfl[base + srcLane] : bits;
+	uint32_t r = (srcLane >= 0 && srcLane < n) ? g_shfl[base + srcLane] : bits;
 	warp_barrier();
 	T out;
 	memcpy(&out, &r, 4);
 	return out;
+}
+static void trampoline() {
+	for (unsigned bz = 0; bz < g_grid.z; ++bz)
+		for (unsigned by = 0; by < g_grid.y; ++by)
+			for (unsigned bx = 0; bx < g_grid.x; ++bx) {
+				blockIdx = uint3{bx, by, bz};
+				g_fn();
+				bar_wait(g_blockBar); // one block at a time: the blocks share the emulated shared memory
+			}
+	const int me = g_cur;
+	g_f[me].done = true;
+	int nx = me;
+	do {
+		nx = nx + 1 == g_T ? 0 : nx + 1;
+	} while (g_f[nx].done && nx != me);
+	if (nx == me) {
+		setcontext(&g_main); // the last fiber returns to the launcher
+	} else {
+		load(nx);
+		setcontext(&g_f[nx].uc);
+	}
 }
 
 template <typename F>
@@ -85,43 +150,44 @@ static void launch(dim3 grid, dim3 block, size_t smemBytes, F fn) {
 	unsigned char *canary = (unsigned char *)dyn_smem + std::min(smemBytes, sizeof(dyn_smem));
 	memset(canary, 0xA5, canaryBytes);
 	const int T = (int)(block.x * block.y * block.z);
-	BlockCtx ctx;
-	pthread_barrier_init(&ctx.blockBar, nullptr, T);
-	int nw = (T + 31) / 32;
-	ctx.warpBar.resize(nw);
-	for (int w = 0; w < nw; ++w) pthread_barrier_init(&ctx.warpBar[w], nullptr, std::min(32, T - 32 * w));
-	ctx.shfl.assign(T, 0);
-	g_ctx = &ctx;
-	std::vector<std::thread> th;
-	th.reserve(T);
+	g_T = T;
+	g_grid = grid;
+	blockDim = block;
+	gridDim = grid;
+	g_fn = fn;
+	g_blockBar = Bar();
+	g_blockBar.n = T;
+	const int nw = (T + 31) / 32;
+	g_warpBar.assign(nw, Bar());
+	for (int w = 0; w < nw; ++w) g_warpBar[w].n = std::min(32, T - 32 * w);
+	g_shfl.assign(T, 0);
+	g_f.resize(T);
+	while ((int)g_stacks.size() < T) g_stacks.push_back((char *)malloc(kStack));
 	for (int t = 0; t < T; ++t) {
-		th.emplace_back([&, t]() {
-			t_tid = t;
-			threadIdx = uint3{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
-			blockDim = block;
-			gridDim = grid;
-			for (unsigned bz = 0; bz < grid.z; ++bz)
-				for (unsigned by = 0; by < grid.y; ++by)
-					for (unsigned bx = 0; bx < grid.x; ++bx) {
-						blockIdx = uint3{bx, by, bz};
-						fn();
-						pthread_barrier_wait(&g_ctx->blockBar);
-					}
-		});
+		Fiber &f = g_f[t];
+		f.done = false;
+		f.tIdx = uint3{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
+		f.bIdx = uint3{0, 0, 0};
+		getcontext(&f.uc);
+		f.uc.uc_stack.ss_sp = g_stacks[t];
+		f.uc.uc_stack.ss_size = kStack;
+		f.uc.uc_link = nullptr;
+		makecontext(&f.uc, trampoline, 0);
 	}
-	for (auto &t : th) t.join();
+	if (T > 0 && grid.x * grid.y * grid.z > 0) {
+		load(0);
+		swapcontext(&g_main, &g_f[0].uc);
+	}
 	for (size_t i = 0; i < canaryBytes; ++i)
 		if (canary[i] != 0xA5) {
 			fprintf(stderr, "cuda_emu: a kernel wrote %zu bytes past its %zu bytes of dynamic shared memory\n", i + 1, smemBytes);
 			abort();
 		}
-	for (int w = 0; w < nw; ++w) pthread_barrier_destroy(&ctx.warpBar[w]);
-	pthread_barrier_destroy(&ctx.blockBar);
-	g_ctx = nullptr;
 }
 } // namespace emu
+static inline void emu_yield() { emu::yield(); }
 
-static inline void __syncthreads() { pthread_barrier_wait(&emu::g_ctx->blockBar); }
+static inline void __syncthreads() { emu::bar_wait(emu::g_blockBar); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
 template <typename T>
 static inline T __shfl_up_sync(unsigned, T v, int d) { return emu::shfl_from(v, (emu::t_tid & 31) - d); }

@@ -128,6 +128,10 @@ PRESET_CALLS = [
     ("default_stereo_0.8x", lambda o: o.presetDefault(2, 48000.0), 2, 0.8, 12800, 5760),  # aligned 16-byte staging, two calls
     ("default_mono_1.25x_odd", lambda o: o.presetDefault(1, 48000.0), 1, 1.25, 12000, 4999),  # unaligned chunks, odd block counts
     ("cheaper_mono_split", lambda o: o.presetCheaper(1, 48000.0), 1, 1.0, 14000, 6000),
+    # the benchmark's call shape: 32 blocks per call, i.e. all 32 lanes of the packed stereo wavefront, two calls
+    ("default_stereo_0.8x_32_blocks_per_call", lambda o: o.presetDefault(2, 48000.0), 2, 0.8, 2 * 57600, 46080),
+    # presetCheaper stereo without transposition: K = 2560, L = 3 (odd lane skew), split computation in the vector overlap-add
+    ("cheaper_stereo_1.5x", lambda o: o.presetCheaper(2, 48000.0), 2, 1.5, 16000, 11520),
 ]
 
 
@@ -141,17 +145,41 @@ def test_preset_pair_kernels_bit_exact_vs_oracle(emu_libs, oracle_port, name, cf
     assert np.array_equal(y, ref), "max diff %g" % np.abs(y - ref).max()
 
 
-def test_fast_chain_arithmetic_stays_within_tolerance(emu_libs, oracle_port):
-    """The default (fast: fused multiply-add, reciprocal / rsqrt) arithmetic of the stereo direct chain against the
-    oracle, FFT substituted: not bit-exact by construction, but within float rounding over a short horizon."""
-    name, cfg, C, ratio, n, chunk = PRESET_CALLS[0]
-    x = signals.batch("harmonic", 1, C, n, 48000)
-    g = _emu(emu_libs["exact"], 1, exact_math=False)
+FULL_SIZE = [
+    # the BASELINE configurations at their real sizes (K = 3072), several calls, two streams
+    ("config1_mono_44k_+12st_ton8k", lambda o: (o.presetDefault(1, 44100.0), o.setTransposeSemitones(12, 8000 / 44100)), 1, 1.0, 30000, 10584),
+    ("config3_mono_+7st_ton8k", lambda o: (o.presetDefault(1, 48000.0), o.setTransposeSemitones(7, 8000 / 48000)), 1, 1.0, 30000, 11520),
+    ("config4_stereo_+12st_formant_comp_200Hz", lambda o: (o.presetDefault(2, 48000.0), o.setTransposeSemitones(12, 0), o.setFormantFactor(1, True), o.setFormantBase(200 / 48000)), 2, 1.0, 30000, 11520),
+    ("config4_auto_pitch", lambda o: (o.presetDefault(2, 48000.0), o.setTransposeSemitones(12, 0), o.setFormantFactor(1, True), o.setFormantBase(0)), 2, 1.0, 30000, 11520),
+    ("config5_cheaper_mono_2x_-5st", lambda o: (o.presetCheaper(1, 48000.0), o.setTransposeSemitones(-5, 0.1)), 1, 2.0, 20000, 15360),
+]
+
+
+@pytest.mark.parametrize("name,cfg,C,ratio,n,chunk", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_baseline_configurations_full_size_bit_exact_vs_oracle(emu_libs, oracle_port, name, cfg, C, ratio, n, chunk):
+    x = signals.batch("harmonic", 2, C, n, 48000)
+    g = _emu(emu_libs["exact"], 2)
     cfg(g)
     y = signals.run_batch(g, x, ratio, chunk)
     ref = _oracle_batch(oracle_port, cfg, x, ratio, chunk)
-    assert not np.array_equal(y, ref)  # the fast path really ran
-    assert rms(y - ref) <= 1e-5 * max(rms(ref), 1e-3) * 10, rms(y - ref)
+    assert np.array_equal(y, ref), "max diff %g" % np.abs(y - ref).max()
+
+
+def test_fast_chain_arithmetic_stays_within_tolerance(emu_libs, oracle_port):
+    """The default (fast: fused multiply-add, reciprocal / rsqrt) arithmetic of the stereo direct chain against the
+    oracle, FFT substituted: not bit-exact by construction, but within float rounding over a short horizon -- also with
+    all 32 lanes of the wavefront busy (32 blocks per call) and with the odd lane skew of presetCheaper."""
+    for name, cfg, C, ratio, n, chunk in (PRESET_CALLS[0], PRESET_CALLS[3], PRESET_CALLS[4]):
+        x = signals.batch("harmonic", 1, C, n, 48000)
+        g = _emu(emu_libs["exact"], 1, exact_math=False)
+        cfg(g)
+        y = signals.run_batch(g, x, ratio, chunk)
+        ref = _oracle_batch(oracle_port, cfg, x, ratio, chunk)
+        assert not np.array_equal(y, ref), name  # the fast path really ran
+        H = g.intervalSamples()
+        head = g.outputLatency() + int(g.inputLatency() * ratio) + 8 * H
+        assert rms((y - ref)[..., :head]) <= 2e-6, (name, rms((y - ref)[..., :head]))  # float rounding over the first blocks
+        assert rms(y - ref) <= 1e-3, (name, rms(y - ref))  # chaotic beyond (SURVEY.md section 0.4): the reference's own -60 dB criterion
 
 
 def test_api_sequence_bit_exact_vs_oracle(emu_libs, oracle_port):
