@@ -283,6 +283,47 @@ def test_unsupported_features_fail_loudly(emu_libs):
         g.set_tuning(99, 0)
 
 
+def test_file_mode_caller_against_the_oracle(emu_libs, oracle_port, tmp_path):
+    """cmd/stretch_cli.cpp (WAV in, the reference tool's outputSeek / process / flush stages through the C++ facade,
+    16-bit WAV out), linked against the emulator build of the library: the file it writes is the oracle's output,
+    driven through the same stages and rounded to 16 bits, sample for sample."""
+    import struct
+
+    exe = os.path.join(os.path.dirname(emu_libs["exact"]), "stretch_cli_emu")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "cmd", "stretch_cli.cpp"),
+                    emu_libs["exact"], "-Wl,-rpath," + os.path.dirname(emu_libs["exact"])], check=True)
+    sr, n, C, semitones, time = 48000, 20000, 1, 4.0, 1.25
+    x = signals.batch("harmonic", 1, C, n, sr)[0]
+    x = (np.round(x * 32768) / 32768).astype(np.float32)
+    src, dst = str(tmp_path / "in.wav"), str(tmp_path / "out.wav")
+    data = np.ascontiguousarray(np.round(x.T * 32768).astype("<i2")).tobytes()  # a 16-bit PCM file, as the reference tool reads
+    with open(src, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, C, sr, sr * C * 2, C * 2, 16))
+        f.write(b"data" + struct.pack("<I", len(data)) + data)
+    r = subprocess.run([exe, src, dst, "--semitones=%g" % semitones, "--time=%g" % time], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d = open(dst, "rb").read()
+    assert d[:4] == b"RIFF" and d[8:12] == b"WAVE" and struct.unpack("<H", d[22:24])[0] == C and struct.unpack("<I", d[24:28])[0] == sr
+    y = np.frombuffer(d[44:], dtype="<i2").reshape(-1, C).T
+    o = oracle_port()
+    o.presetDefault(C, float(sr))
+    o.setTransposeSemitones(semitones, 8000.0 / sr)
+    o.setFormantSemitones(0.0, False)
+    o.setFormantBase(100.0 / sr)
+    n_out = int(round(n * time))
+    seek = o.outputSeekLength(np.float32(1 / time))
+    out_index = n_out - o.intervalSamples()
+    in_index = int(round((out_index + o.outputLatency()) / time)) + o.inputLatency()
+    xp = np.zeros((C, max(in_index, seek)), np.float32)
+    xp[:, :n] = x
+    o.outputSeek(xp[:, :seek])
+    ref = np.concatenate([o.process(xp[:, seek:in_index], out_index), o.flush(n_out - out_index)], axis=1)
+    v = ref * np.float32(32768.0)
+    q = np.clip(np.sign(v) * np.floor(np.abs(v) + np.float32(0.5)), -32768, 32767).astype(np.int16)  # std::round: halves away from zero
+    assert y.shape == q.shape
+    assert np.array_equal(y, q), "max diff %d LSB" % np.abs(y.astype(np.int32) - q).max()
+
+
 # ------------------------------------------------------------------ sharding, gloo world_size 2
 def test_shard_range_partitions_the_batch():
     from signalsmith_stretch_b200.shard import shard_range
