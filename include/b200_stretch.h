@@ -104,6 +104,10 @@ int b200s_process(b200s_engine *e, const float *in, int input_samples, float *ou
  * be read until b200s_synchronize() (or any synchronous call) returns; pinned host memory is needed for the copies to
  * be asynchronous at all. */
 int b200s_process_async(b200s_engine *e, const float *in, int input_samples, float *out, int output_samples);
+/* The same call with 16-bit PCM host buffers (what the reference's command-line tool reads and writes, cmd/util/wav.h):
+ * sample / 32768 on the way in, round-to-nearest and clamp on the way out, both on the device, so that only two bytes
+ * per sample cross PCIe -- the path is PCIe-bound end to end.  wait = 0: asynchronous like b200s_process_async. */
+int b200s_process_pcm16(b200s_engine *e, const short *in, int input_samples, short *out, int output_samples, int wait);
 int b200s_flush(b200s_engine *e, float *out, int output_samples, float playback_rate);
 int b200s_exact(b200s_engine *e, const float *in, int input_samples, float *out, int output_samples, int *ok);
 /* Device-buffer variants: pointers are device memory on the handle's GPU, same planar layout;

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "b200s_fft_samples", "b200s_bands",
     "b200s_set_transpose_factor", "b200s_set_transpose_semitones", "b200s_set_formant_factor",
     "b200s_set_formant_semitones", "b200s_set_formant_base", "b200s_set_freq_map_table",
-    "b200s_seek", "b200s_output_seek", "b200s_process", "b200s_process_async", "b200s_flush", "b200s_exact",
+    "b200s_seek", "b200s_output_seek", "b200s_process", "b200s_process_async", "b200s_process_pcm16", "b200s_flush", "b200s_exact",
     "b200s_seek_device", "b200s_process_device", "b200s_flush_device",
     "b200s_timer_start", "b200s_timer_stop", "b200s_kernel_launches", "b200s_profile_begin", "b200s_profile_end",
     "b200s_selftest_divsqrt",
@@ -82,7 +82,7 @@ def _bind(lib):
         "b200s_set_formant_factor": (ci, [vp, cf, ci]), "b200s_set_formant_semitones": (ci, [vp, cf, ci]),
         "b200s_set_formant_base": (ci, [vp, cf]), "b200s_set_freq_map_table": (ci, [vp, fp, fp, ci]),
         "b200s_seek": (ci, [vp, vp, ci, cd]), "b200s_output_seek": (ci, [vp, vp, ci]),
-        "b200s_process": (ci, [vp, vp, ci, vp, ci]), "b200s_process_async": (ci, [vp, vp, ci, vp, ci]), "b200s_flush": (ci, [vp, vp, ci, cf]),
+        "b200s_process": (ci, [vp, vp, ci, vp, ci]), "b200s_process_async": (ci, [vp, vp, ci, vp, ci]), "b200s_process_pcm16": (ci, [vp, vp, ci, vp, ci, ci]), "b200s_flush": (ci, [vp, vp, ci, cf]),
         "b200s_exact": (ci, [vp, vp, ci, vp, ci, ip]),
         "b200s_seek_device": (ci, [vp, vp, ci, cd]), "b200s_process_device": (ci, [vp, vp, ci, vp, ci]),
         "b200s_flush_device": (ci, [vp, vp, ci, cf]),
@@ -272,6 +272,17 @@ class BatchStretch:
     def process_host_ptr_async(self, in_ptr, n_in, out_ptr, n_out):
         """b200s_process_async: enqueue and return; buffers (pinned) belong to the engine until synchronize()."""
         self._ck(self._lib.b200s_process_async(self._h, in_ptr, n_in, out_ptr, n_out))
+
+    def process_pcm16(self, inputs, outputSamples):
+        """16-bit PCM in / out (int16 arrays [batch][channels][n]); conversion on the device."""
+        x = np.ascontiguousarray(inputs, dtype=np.int16)
+        n_in = x.shape[-1]
+        out = np.empty(self._shape(max(outputSamples, 0)), np.int16)
+        self._ck(self._lib.b200s_process_pcm16(self._h, x.ctypes.data, n_in, out.ctypes.data, outputSamples, 1))
+        return out
+
+    def process_pcm16_ptr(self, in_ptr, n_in, out_ptr, n_out, wait=False):
+        self._ck(self._lib.b200s_process_pcm16(self._h, in_ptr, n_in, out_ptr, n_out, 1 if wait else 0))
 
     def flush(self, outputSamples, playbackRate=0.0):
         out = np.empty(self._shape(max(outputSamples, 0)), np.float32)

@@ -80,6 +80,8 @@ struct b200s_engine {
 	// staging for the host-buffer API and for flush/outputSeek
 	float *dIn = 0, *dOut = 0, *dZero = 0, *dTmp = 0;
 	size_t inCap = 0, outCap = 0, zeroCap = 0, tmpCap = 0;
+	short *dIn16 = 0, *dOut16 = 0; // 16-bit PCM staging of b200s_process_pcm16
+	size_t in16Cap = 0, out16Cap = 0;
 };
 
 #define CK(call)                                                                                   \
@@ -122,7 +124,8 @@ static void free_all(b200s_engine *e) {
 	dfree(e->dSched); dfree(e->dHist[0]); dfree(e->dHist[1]); dfree(e->dPend); dfree(e->dPendWp);
 	dfree(e->dStIn); dfree(e->dStPrev); dfree(e->dStOut); dfree(e->dStPredE); dfree(e->dStIl);
 	dfree(e->dFrames); dfree(e->dCall); dfree(e->dJobs); dfree(e->dSpec); dfree(e->dY); dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dE); dfree(e->dStPitch); dfree(e->dPitch);
-	dfree(e->dIn); dfree(e->dOut); dfree(e->dZero); dfree(e->dTmp);
+	dfree(e->dIn); dfree(e->dOut); dfree(e->dZero); dfree(e->dTmp); dfree(e->dIn16); dfree(e->dOut16);
+	e->in16Cap = e->out16Cap = 0;
 	e->maxFrames = 0;
 	e->inCap = e->outCap = e->zeroCap = e->tmpCap = 0;
 }
@@ -508,7 +511,7 @@ static int ensure_buf(b200s_engine *e, float **p, size_t *cap, size_t n, bool ze
 // PCIe transfers of one group overlap the kernels of the others.
 static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, long long inStreamStride, int nIn,
                         float *dOut, int outChanStride, long long outStreamStride, int nOut,
-                        const float *hIn = nullptr, float *hOut = nullptr) {
+                        const float *hIn = nullptr, float *hOut = nullptr, const short *hIn16 = nullptr, short *hOut16 = nullptr) {
 	const Cfg &g = e->cfg;
 	if (nIn < 0 || nOut < 0) {
 		e->err = "process: negative sample count";
@@ -527,7 +530,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	// sub-batch 1 is still in its FFT kernel, and so on: the latency-bound wavefront kernel and the
 	// throughput-bound FFT kernels share the SMs instead of taking turns.  Per-kernel profiling
 	// (b200s_profile_begin) runs unsplit on the main stream so that the event pairs time one kernel each.
-	const bool hostIO = hIn || hOut;
+	const bool hostIO = hIn || hOut || hIn16 || hOut16;
 	const int wantSub = hostIO ? e->nHostParts : e->nSub;
 	// (host-buffer pipeline: at least two streams per group; device-resident sub-batches: only for large batches)
 	const int nSub = (e->profiling || wantSub <= 1 || g.S < (hostIO ? 2 * wantSub : 64)) ? 1 : std::min(wantSub, e->maxSub);
@@ -550,6 +553,12 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 		x.sCount = (int)((long long)g.S * (sub + 1) / nSub) - x.sBase;
 		if (hIn && nIn > 0)
 			CK(cudaMemcpyAsync((float *)dIn + (size_t)x.sBase * g.C * nIn, hIn + (size_t)x.sBase * g.C * nIn, sizeof(float) * (size_t)x.sCount * g.C * nIn, cudaMemcpyHostToDevice, st));
+		if (hIn16 && nIn > 0) { // 16-bit PCM: 2 bytes per sample over PCIe, converted on the device
+			const size_t off = (size_t)x.sBase * g.C * nIn, cnt = (size_t)x.sCount * g.C * nIn;
+			CK(cudaMemcpyAsync(e->dIn16 + off, hIn16 + off, sizeof(short) * cnt, cudaMemcpyHostToDevice, st));
+			B200S_LAUNCH(k_pcm16_in, dim3((unsigned)std::min<size_t>((cnt + 1023) / 1024, 4096)), dim3(256), 0, st, e->dIn16 + off, (float *)dIn + off, cnt);
+			CKL();
+		}
 		{ // (profiling implies nSub == 1, i.e. st == e->stream, which is where PROF() records its events)
 			PROF(PK_PLAN, B200S_LAUNCH(k_plan, dim3(x.sCount), dim3(kThreads), 0, st, x));
 			if (F > 0) {
@@ -592,6 +601,12 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 		}
 		if (hOut && nOut > 0)
 			CK(cudaMemcpyAsync(hOut + (size_t)x.sBase * g.C * nOut, dOut + (size_t)x.sBase * g.C * nOut, sizeof(float) * (size_t)x.sCount * g.C * nOut, cudaMemcpyDeviceToHost, st));
+		if (hOut16 && nOut > 0) {
+			const size_t off = (size_t)x.sBase * g.C * nOut, cnt = (size_t)x.sCount * g.C * nOut;
+			B200S_LAUNCH(k_pcm16_out, dim3((unsigned)std::min<size_t>((cnt + 1023) / 1024, 4096)), dim3(256), 0, st, dOut + off, e->dOut16 + off, cnt);
+			CKL();
+			CK(cudaMemcpyAsync(hOut16 + off, e->dOut16 + off, sizeof(short) * cnt, cudaMemcpyDeviceToHost, st));
+		}
 		if (nSub > 1) {
 			CK(cudaEventRecord(e->evSubDone[sub], st));
 			CK(cudaStreamWaitEvent(e->stream, e->evSubDone[sub], 0));
@@ -890,6 +905,26 @@ int b200s_process(b200s_engine *e, const float *in, int nIn, float *out, int nOu
 	if ((rc = stage_out(e, nOut))) return rc;
 	if ((rc = process_impl(e, e->dIn, nIn, (long long)e->cfg.C * nIn, nIn, e->dOut, nOut, (long long)e->cfg.C * nOut, nOut, in, out))) return rc;
 	CK(cudaStreamSynchronize(e->stream));
+	return 0;
+}
+// 16-bit PCM host buffers (asynchronous like b200s_process_async when `wait` is 0)
+int b200s_process_pcm16(b200s_engine *e, const short *in, int nIn, short *out, int nOut, int wait) {
+	NEED_CFG();
+	int rc;
+	const size_t ci = (size_t)e->cfg.S * e->cfg.C * std::max(nIn, 1), co = (size_t)e->cfg.S * e->cfg.C * std::max(nOut, 1);
+	if (ci > e->inCap || co > e->outCap || ci > e->in16Cap || co > e->out16Cap || !e->dIn || !e->dOut) CK(cudaStreamSynchronize(e->stream)); // staging grows: drain first
+	if ((rc = stage_in(e, nullptr, nIn))) return rc;
+	if ((rc = stage_out(e, nOut))) return rc;
+	if (ci > e->in16Cap) {
+		if ((rc = dalloc(e, &e->dIn16, ci))) return rc;
+		e->in16Cap = ci;
+	}
+	if (co > e->out16Cap) {
+		if ((rc = dalloc(e, &e->dOut16, co))) return rc;
+		e->out16Cap = co;
+	}
+	if ((rc = process_impl(e, e->dIn, nIn, (long long)e->cfg.C * nIn, nIn, e->dOut, nOut, (long long)e->cfg.C * nOut, nOut, nullptr, nullptr, in, out))) return rc;
+	if (wait) CK(cudaStreamSynchronize(e->stream));
 	return 0;
 }
 int b200s_process_async(b200s_engine *e, const float *in, int nIn, float *out, int nOut) {

@@ -355,3 +355,31 @@ def test_paired_fft_kernels_match_scalar_fft_kernels(gpu):
         x = signals.batch("harmonic", 3, 2, 48000, 48000)
         outs.append(signals.run_batch(e, x, 1.0, 7200))
     assert rms(outs[0] - outs[1]) <= 2e-7
+
+
+@pytest.mark.gpu
+def test_pcm16_boundary_equals_float_path_with_the_tools_conversions(gpu):
+    """b200s_process_pcm16 (int16 over PCIe, conversions on the device) == the float call fed sample / 32768 with its
+    output rounded to nearest (halves away from zero) and clamped; several calls, stream groups chained."""
+    cfg, C, sr, ratio, kind = signals.CONFIGS["config2_stereo_0p8x"]
+    S = 48
+    outs = []
+    for pcm in (True, False):
+        e = gpu(S)
+        cfg(e)
+        H = e.intervalSamples()
+        n_out = 6 * H
+        n_in = int(round(n_out / ratio))
+        x = signals.batch(kind, S, C, 3 * n_in, sr)
+        x16 = np.clip(np.round(x * 32768), -32768, 32767).astype(np.int16)
+        ys = []
+        for k in range(3):
+            chunk = np.ascontiguousarray(x16[:, :, k * n_in:(k + 1) * n_in])
+            if pcm:
+                ys.append(e.process_pcm16(chunk, n_out))
+            else:
+                v = e.process(chunk.astype(np.float32) * np.float32(1 / 32768), n_out) * np.float32(32768)
+                ys.append(np.clip(np.sign(v) * np.floor(np.abs(v) + np.float32(0.5)), -32768, 32767).astype(np.int16))
+        outs.append(np.concatenate(ys, axis=2))
+    assert np.abs(outs[0]).max() > 300
+    assert np.array_equal(outs[0], outs[1])

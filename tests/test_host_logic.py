@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(cuda_lib):
     import signalsmith_stretch_b200 as pkg
 
     header = open(os.path.join(ROOT, "include", "b200_stretch.h")).read()
-    declared = sorted(set(re.findall(r"\b(b200s_[a-z_]+)\s*\(", header)))
+    declared = sorted(set(re.findall(r"\b(b200s_[a-z0-9_]+)\s*\(", header)))
     assert declared == sorted(pkg.ABI_SYMBOLS)
     lib = ctypes.CDLL(cuda_lib)
     for name in declared:
@@ -237,6 +237,30 @@ def test_async_host_calls_equal_blocking_calls(emu_libs):
                 g.process_host_ptr(xi.ctypes.data, 256, ys[k].ctypes.data, 256)
         g.synchronize()
         outs.append(np.concatenate(ys, axis=2))
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_pcm16_boundary_equals_float_path_with_the_tools_conversions(emu_libs):
+    """b200s_process_pcm16: int16 in / out with the conversions on the device == the float call fed sample / 32768,
+    its output rounded to nearest (halves away from zero) and clamped -- what the reference's tool does around the path."""
+    x = signals.batch("harmonic", 4, 2, 3 * 640, 48000)
+    x16 = np.clip(np.round(x * 32768), -32768, 32767).astype(np.int16)
+    outs = []
+    for pcm in (True, False):
+        g = _emu(emu_libs["float"], 4)
+        g.set_tuning(2, 2)  # two stream groups
+        g.configure(2, 512, 128)
+        g.setTransposeSemitones(-2, 0.3)
+        ys = []
+        for k in range(3):
+            chunk = np.ascontiguousarray(x16[:, :, 640 * k:640 * (k + 1)])
+            if pcm:
+                ys.append(g.process_pcm16(chunk, 640))
+            else:
+                v = g.process((chunk.astype(np.float32) * np.float32(1 / 32768)), 640) * np.float32(32768)
+                ys.append(np.clip(np.sign(v) * np.floor(np.abs(v) + np.float32(0.5)), -32768, 32767).astype(np.int16))
+        outs.append(np.concatenate(ys, axis=2))
+    assert np.abs(outs[0]).max() > 300
     assert np.array_equal(outs[0], outs[1])
 
 
