@@ -242,6 +242,39 @@ def run_reference_arm(args, rank, world):
                       "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+# ------------------------------------------------------------------------------------ 16-bit PCM boundary probe
+def pcm16_probe(args):
+    """Child process of the default run (never the measured arm itself): the same workload through
+    b200s_process_pcm16 -- int16 host buffers, conversions on the device, half the PCIe bytes -- streamed like `e2e`."""
+    import torch
+
+    from signalsmith_stretch_b200 import BatchStretch, build_library
+
+    build_library()
+    torch.cuda.set_device(0)
+    w = workload(args.batch)
+    eng = BatchStretch(args.batch, device=0)
+    eng.presetDefault(CHANNELS, float(SR))
+    eng.reserve(w["n_in"], w["n_out"])
+    pool = synth_input(min(args.batch, 64), 3 * w["n_in"])
+    x = np.tile(pool, ((args.batch + len(pool) - 1) // len(pool), 1, 1))[:args.batch]
+    x16 = np.clip(np.round(x * 32768), -32768, 32767).astype(np.int16)
+    xs = [torch.from_numpy(np.ascontiguousarray(x16[:, :, k * w["n_in"]:(k + 1) * w["n_in"]])).pin_memory() for k in range(3)]
+    ys = [torch.empty((args.batch, CHANNELS, w["n_out"]), dtype=torch.int16).pin_memory() for _ in range(3)]
+    for i in range(3):
+        eng.process_pcm16_ptr(xs[i % 3].data_ptr(), w["n_in"], ys[i % 3].data_ptr(), w["n_out"], wait=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        eng.process_pcm16_ptr(xs[i % 3].data_ptr(), w["n_in"], ys[i % 3].data_ptr(), w["n_out"], wait=False)
+    eng.synchronize()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(json.dumps({"value": w["samples_per_step"] * args.steps / dt, "unit": "samples/s", "ms_per_step": dt / args.steps * 1e3,
+                      "h2d_bytes_per_step": int(xs[0].numel() * 2), "d2h_bytes_per_step": int(ys[0].numel() * 2),
+                      "timed": "host wall clock around %d pipelined b200s_process_pcm16() calls + synchronize (int16 host buffers, conversions on the device)" % args.steps}))
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -254,7 +287,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs (ncu): device-resident steps only; the JSON line then has no e2e / per-kernel split")
     ap.add_argument("--sub-batches", type=int, default=0, help="device-resident path: split the batch over N prioritised CUDA streams (experiment)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4], help="BASELINE config (default 2 = the headline)")
+    ap.add_argument("--pcm16-probe", action="store_true", help="internal: child process measuring the 16-bit PCM boundary")
     args = ap.parse_args()
+    if args.pcm16_probe:
+        pcm16_probe(args)
+        return
     if args.config != 2:
         global CHANNELS, RATIO_OUT, ALGO_BYTES_PER_BLOCK_CHANNEL
         CHANNELS, RATIO_OUT, ALGO_BYTES_PER_BLOCK_CHANNEL = EXTRA[args.config]["channels"], 1.0, EXTRA[args.config]["algo"]
@@ -406,13 +443,24 @@ def main():
         threads = os.cpu_count() or 1
         cpu = cpu_reference_run(max(8 * threads, 64), 5.0, threads)
 
+    # the 16-bit PCM boundary (not the reference's float call: reported beside `e2e`, never instead of it), measured in a
+    # child process so that nothing it does can take the line above with it
+    e2e_pcm16 = None
+    if rank == 0 and world == 1 and args.config == 2:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--pcm16-probe", "--steps", str(args.steps), "--batch", str(args.batch)],
+                               capture_output=True, text=True, timeout=240)
+            e2e_pcm16 = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"unavailable": (r.stderr or "failed")[-200:]}
+        except Exception as ex:  # noqa: BLE001
+            e2e_pcm16 = {"unavailable": str(ex)[-200:]}
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tmax / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": dict(config_dict(w, world), **({} if args.config == 2 else {"workload": EXTRA[args.config]["name"]})), "clocks": clk,
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}))
+            "e2e": e2e, "e2e_pcm16": e2e_pcm16, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
 
