@@ -165,6 +165,62 @@ def test_baseline_configurations_full_size_bit_exact_vs_oracle(emu_libs, oracle_
     assert np.array_equal(y, ref), "max diff %g" % np.abs(y - ref).max()
 
 
+def test_parameters_change_between_calls_bit_exact_vs_oracle(emu_libs, oracle_port):
+    """Switching between the kernel paths from call to call -- plain stereo (packed direct chain on interleaved spectra,
+    state carried through k_plan / k_commit in both layouts), frequency map (k_prep + generic chain), formants with
+    automatic pitch, back to plain, a time-stretch change -- must carry every piece of state across: same sequence on
+    the oracle, bit for bit."""
+    x = signals.batch("harmonic", 1, 2, 8 * 5760, 48000)
+
+    def seq(o, wrap, unwrap):
+        o.presetDefault(2, 48000.0)
+        outs, pos = [], 0
+
+        def run(n_in, n_out):
+            nonlocal pos
+            outs.append(unwrap(o.process(wrap(x[0][:, pos:pos + n_in]), n_out)))
+            pos += n_in
+
+        run(5760, 5760)
+        run(7200, 5760)              # 0.8x: re-analysis every block
+        o.setTransposeSemitones(3, 0.2)
+        run(5760, 5760)              # mapped
+        o.setFormantFactor(1.2, True)
+        o.setFormantBase(0)
+        run(5760, 5760)              # mapped + formants, automatic pitch
+        run(2880, 5760)              # 2x stretch with formants
+        o.setTransposeSemitones(0, 0)
+        o.setFormantFactor(1, False)
+        run(5760, 5760)              # plain again: interleaved state rebuilt from the planar one
+        run(7200, 5760)
+        return np.concatenate(outs, axis=1)
+
+    ref = seq(oracle_port(), lambda a: a, lambda a: a)
+    got = seq(_emu(emu_libs["exact"], 1), lambda a: a[None], lambda a: np.asarray(a)[0])
+    assert np.array_equal(ref, got), "max diff %g" % np.abs(ref - got).max()
+
+
+def test_silence_bypass_and_energy_scan_at_preset_size_bit_exact_vs_oracle(emu_libs, oracle_port):
+    """Stereo preset path through silence: the energy scan of k_plan (which stops at the first loud tile), the silence
+    counter, the first bypass call that zeroes the spectra (also their interleaved copies), bypass copies, and the
+    restart -- including a chunk that is silent except for its last samples (the scan must not stop early there)."""
+    x = signals.batch("harmonic", 1, 2, 6 * 5760, 48000)[0]
+    z = np.zeros((2, 5760), np.float32)
+    late = z.copy()
+    late[:, -7:] = 0.25  # loud only at the very end of the chunk
+
+    def seq(o, wrap, unwrap):
+        o.presetDefault(2, 48000.0)
+        outs = []
+        for chunk in (x[:, :5760], x[:, 5760:11520], z, z, z, z[:, :2880], late, z, x[:, 11520:17280], x[:, 17280:23040]):
+            outs.append(unwrap(o.process(wrap(chunk), 5760)))
+        return np.concatenate(outs, axis=1)
+
+    ref = seq(oracle_port(), lambda a: a, lambda a: a)
+    got = seq(_emu(emu_libs["exact"], 1), lambda a: a[None], lambda a: np.asarray(a)[0])
+    assert np.array_equal(ref, got), "max diff %g" % np.abs(ref - got).max()
+
+
 def test_fast_chain_arithmetic_stays_within_tolerance(emu_libs, oracle_port):
     """The default (fast: fused multiply-add, reciprocal / rsqrt) arithmetic of the stereo direct chain against the
     oracle, FFT substituted: not bit-exact by construction, but within float rounding over a short horizon -- also with
