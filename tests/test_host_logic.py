@@ -132,6 +132,10 @@ PRESET_CALLS = [
     ("default_stereo_0.8x_32_blocks_per_call", lambda o: o.presetDefault(2, 48000.0), 2, 0.8, 2 * 57600, 46080),
     # presetCheaper stereo without transposition: K = 2560, L = 3 (odd lane skew), split computation in the vector overlap-add
     ("cheaper_stereo_1.5x", lambda o: o.presetCheaper(2, 48000.0), 2, 1.5, 16000, 11520),
+    # more than 32 blocks per call: a second group of lanes whose first block takes its predecessor from the rows the
+    # first group wrote (stereo), several warps per stream handing over through shared memory (mono)
+    ("default_stereo_1.25x_40_blocks_per_call", lambda o: o.presetDefault(2, 48000.0), 2, 1.25, 2 * 46080, 57600),
+    ("default_mono_0.8x_40_blocks_per_call", lambda o: o.presetDefault(1, 48000.0), 1, 0.8, 2 * 72000, 57600),
 ]
 
 
@@ -318,6 +322,34 @@ def test_pcm16_boundary_equals_float_path_with_the_tools_conversions(emu_libs):
         outs.append(np.concatenate(ys, axis=2))
     assert np.abs(outs[0]).max() > 300
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_api_sequence_at_preset_size_stereo_bit_exact_vs_oracle(emu_libs, oracle_port):
+    """seek / process / flush / reset / outputSeek / exact on the stereo preset kernels (paired FFT, packed chain, ring
+    in shared memory): the state these calls touch lives in the layouts of the preset path."""
+    x = signals.batch("harmonic", 1, 2, 60000, 48000)[0]
+
+    def seq(o, wrap, unwrap):
+        o.presetDefault(2, 48000.0)
+        outs = []
+        o.seek(wrap(x[:, :3000]), 1.25)
+        outs.append(unwrap(o.process(wrap(x[:, 3000:10200]), 5760)))
+        outs.append(unwrap(o.process(wrap(x[:, 10200:13800]), 2880)))
+        outs.append(unwrap(o.flush(1000, 1.0)))
+        outs.append(unwrap(o.process(wrap(x[:, 14000:19760]), 5760)))
+        outs.append(unwrap(o.flush(7000, 1.2)))
+        o.reset()
+        outs.append(unwrap(o.process(wrap(x[:, 20000:22880]), 2880)))
+        o.outputSeek(wrap(x[:, 23000:23000 + o.outputSeekLength(0.8)]))
+        outs.append(unwrap(o.process(wrap(x[:, 30000:34608]), 5760)))
+        ok, e = o.exact(wrap(x[:, 35000:55000]), 16000)
+        assert ok
+        outs.append(unwrap(e))
+        return np.concatenate(outs, axis=1)
+
+    ref = seq(oracle_port(), lambda a: a, lambda a: a)
+    got = seq(_emu(emu_libs["exact"], 1), lambda a: a[None], lambda a: np.asarray(a)[0])
+    assert np.array_equal(ref, got), "max diff %g" % np.abs(ref - got).max()
 
 
 def test_streams_are_independent_and_chunking_is_invariant(emu_libs):
