@@ -70,6 +70,7 @@ static std::vector<char *> g_stacks;
 static const size_t kStack = 512 * 1024;
 static ucontext_t g_main;
 static int g_cur = 0, g_T = 0;
+static unsigned long long g_seed = getenv("B200S_EMU_SEED") ? strtoull(getenv("B200S_EMU_SEED"), nullptr, 10) : 0ull;
 static Bar g_blockBar;
 static std::vector<Bar> g_warpBar;
 static std::vector<uint32_t> g_shfl;
@@ -89,6 +90,12 @@ static inline void yield() {
 	g_f[from].tIdx = threadIdx;
 	g_f[from].bIdx = blockIdx;
 	int nx = from;
+	if (g_seed) { // B200S_EMU_SEED: pseudo-random choice of the next fiber, to shake out order-dependent code
+		g_seed = g_seed * 6364136223846793005ull + 1442695040888963407ull;
+		nx = (int)((g_seed >> 33) % (unsigned)g_T);
+		if (nx == from) nx = nx + 1 == g_T ? 0 : nx + 1;
+		nx = nx == 0 ? g_T - 1 : nx - 1; // the loop below starts one after nx
+	}
 	do {
 		nx = nx + 1 == g_T ? 0 : nx + 1;
 	} while (g_f[nx].done && nx != from);

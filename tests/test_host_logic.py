@@ -225,6 +225,21 @@ def test_silence_bypass_and_energy_scan_at_preset_size_bit_exact_vs_oracle(emu_l
     assert np.array_equal(ref, got), "max diff %g" % np.abs(ref - got).max()
 
 
+def test_streams_with_different_schedules_in_one_batch_bit_exact_vs_oracle(emu_libs, oracle_port):
+    """One launch sequence, diverging streams: stream 1 falls silent (silence counter, then bypass: no analysis jobs, no
+    blocks) and comes back while streams 0 and 2 keep going -- the persistent analysis kernel has to skip the job slots
+    of the bypassed stream (items looked up two ahead), every kernel its empty block list."""
+    S, C, calls, n = 3, 2, 9, 5760
+    x = signals.batch("harmonic", S, C, calls * n, 48000)
+    x[1, :, 2 * n:7 * n] = 0.0  # stream 1: silent for five calls
+    g = _emu(emu_libs["exact"], S)
+    g.presetDefault(C, 48000.0)
+    y = signals.run_batch(g, x, 1.0, n)
+    ref = _oracle_batch(oracle_port, lambda o: o.presetDefault(C, 48000.0), x, 1.0, n)
+    for s_ in range(S):
+        assert np.array_equal(y[s_], ref[s_]), "stream %d: max diff %g" % (s_, np.abs(y[s_] - ref[s_]).max())
+
+
 def test_fast_chain_arithmetic_stays_within_tolerance(emu_libs, oracle_port):
     """The default (fast: fused multiply-add, reciprocal / rsqrt) arithmetic of the stereo direct chain against the
     oracle, FFT substituted: not bit-exact by construction, but within float rounding over a short horizon -- also with
