@@ -240,6 +240,55 @@ def test_streams_with_different_schedules_in_one_batch_bit_exact_vs_oracle(emu_l
         assert np.array_equal(y[s_], ref[s_]), "stream %d: max diff %g" % (s_, np.abs(y[s_] - ref[s_]).max())
 
 
+def test_randomised_configurations_bit_exact_vs_oracle(emu_libs, oracle_port):
+    """Differential fuzz, fixed seed: random sizes (generic kernels) and presets at several sample rates (paired-FFT
+    kernels, K = 3072 / 2560 / other), mono / stereo, split or not, time ratios, transposition with and without
+    tonality limit, formants with fixed and automatic pitch, aligned and odd chunk sizes -- bit for bit against the
+    oracle.  (Ratios whose time factor exceeds 2 are left out: the reference draws random numbers there)"""
+    rng = np.random.default_rng(2024)
+    for it in range(36):
+        preset = it % 3 == 2
+        C = int(rng.integers(1, 3))
+        split = bool(rng.integers(0, 2))
+        ratio = float(rng.choice([0.5, 0.75, 0.8, 1.0, 1.25, 1.5, 1.8]))
+        semis = float(rng.choice([0, 0, 3, -4, 7, 12]))
+        ton = float(rng.choice([0, 0.1, 0.25]))
+        form = int(rng.choice([0, 0, 1, 2, 3]))
+        if preset:
+            sr = float(rng.choice([32000, 40000, 44100, 48000]))
+            cheaper = bool(rng.integers(0, 2))
+            H = int(sr * (0.04 if cheaper else 0.03))
+            chunk = int(rng.choice([H * 4, H * 3 + 5, H * 2 + 1, 4 * (H // 2)]))
+            conf = lambda o: (o.presetCheaper if cheaper else o.presetDefault)(C, sr, split)  # noqa: E731
+        else:
+            sr = 48000.0
+            block = int(rng.choice([256, 320, 384, 400, 512, 640, 768, 1000, 1024]))
+            interval = int(block // rng.choice([3, 4, 5, 6]))
+            chunk = int(rng.choice([interval * 2, interval * 3 + 7, 480, 1000, block * 2]))
+            conf = lambda o: o.configure(C, block, interval, split)  # noqa: E731
+
+        def cfg(o):
+            conf(o)
+            o.setTransposeSemitones(semis, ton)
+            if form == 1:
+                o.setFormantFactor(1, True)
+                o.setFormantBase(200 / sr)
+            elif form == 2:
+                o.setFormantSemitones(3, False)
+                o.setFormantBase(300 / sr)
+            elif form == 3:
+                o.setFormantSemitones(-2, True)
+                o.setFormantBase(0)
+
+        n_out = chunk * int(rng.integers(2, 4))
+        x = signals.batch("harmonic", 1, C, int(round(n_out / ratio)) + 8, int(sr))
+        g = _emu(emu_libs["exact"], 1)
+        cfg(g)
+        y = signals.run_batch(g, x, ratio, chunk)
+        ref = _oracle_batch(oracle_port, cfg, x, ratio, chunk)
+        assert np.array_equal(y, ref), (it, preset, C, sr, split, ratio, semis, ton, form, chunk, float(np.abs(y - ref).max()))
+
+
 def test_fast_chain_arithmetic_stays_within_tolerance(emu_libs, oracle_port):
     """The default (fast: fused multiply-add, reciprocal / rsqrt) arithmetic of the stereo direct chain against the
     oracle, FFT substituted: not bit-exact by construction, but within float rounding over a short horizon -- also with
