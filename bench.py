@@ -161,14 +161,84 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
+# ------------------------------------------------------------------------------------ host cores / NUMA
+def host_cores():
+    """The CPUs this process may actually use: affinity mask, cgroup CPU quota, physical cores (os.cpu_count() is none
+    of these: on a leased box it reports every logical CPU of the host)."""
+    aff = sorted(os.sched_getaffinity(0))
+    quota = None
+    try:  # cgroup v2
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:  # cgroup v1
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    phys = set()
+    try:
+        cur = {}
+        for ln in list(open("/proc/cpuinfo")) + [""]:
+            if ":" in ln:
+                k, v = [t.strip() for t in ln.split(":", 1)]
+                cur[k] = v
+            elif not ln.strip() and cur:
+                if int(cur.get("processor", -1)) in aff:
+                    phys.add((cur.get("physical id", "0"), cur.get("core id", cur.get("processor"))))
+                cur = {}
+    except Exception:
+        pass
+    usable = len(aff)
+    if quota is not None:
+        usable = max(1, min(usable, int(quota + 0.5)))
+    return {"logical_cpus": os.cpu_count(), "affinity_cpus": len(aff), "cgroup_quota_cpus": quota,
+            "physical_cores_in_affinity": len(phys) or None, "usable": usable}
+
+
+def bind_to_gpu_numa(index):
+    """Pin this rank (and therefore the first-touch placement of the pinned host buffers it allocates afterwards) to
+    the CPUs local to its GPU.  GPUs 0-3 / 4-7 of an 8-GPU HGX box hang off different sockets; without this every rank's
+    staging memory lands on whichever node the launcher ran on and half of the PCIe traffic crosses the socket link."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = ((os.cpu_count() or 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cur = os.sched_getaffinity(0)
+        want = cpus & cur
+        info["gpu_local_cpus"] = len(cpus)
+        try:
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            info["numa_node"] = int(open("/sys/bus/pci/devices/%s/numa_node" % bus.lower()[-12:]).read())
+        except Exception:
+            info["numa_node"] = None
+        if want and want != cur:
+            os.sched_setaffinity(0, want)
+            info["bound"] = True
+        info["cpus_after"] = len(os.sched_getaffinity(0))
+    except Exception as ex:  # noqa: BLE001
+        info["error"] = str(ex)[-120:]
+    return info
+
+
 # ------------------------------------------------------------------------------------ CPU reference
 _CPU_INPUT = {}
 
 
-def cpu_reference_run(n_streams, seconds_per_stream, threads):
+def cpu_reference_run(n_streams, seconds_per_stream, threads, fast=False):
     """The reference's own implementation of this workload on the host cores.
-    kind "reference": the shipped WASM binary translated to C (oracle/_ref/libwasm_stretch.so);
-    falls back to the oracle restatement ("port") only if that file is absent."""
+    kind "reference": the shipped WASM binary translated to C (oracle/_ref/libwasm_stretch.so, gcc -O2 -ffp-contract=off;
+    fast=True: the same translation built -O3 -ffast-math -mavx2 -mfma, BASELINE.md section 3);
+    falls back to the oracle restatement ("port") only if that file is absent.
+    Timed: the process() calls only (instance creation and presetDefault excluded), wall clock of the thread pool."""
     import ctypes
 
     from oracle import hdrref, wasmref
@@ -185,16 +255,23 @@ def cpu_reference_run(n_streams, seconds_per_stream, threads):
         _CPU_INPUT["x"] = np.ascontiguousarray(np.tile(pool, ((n_streams + len(pool) - 1) // len(pool), 1, 1))[:n_streams])
         _CPU_INPUT["key"] = key
     x = _CPU_INPUT["x"]
-    if wasmref.available():
+    wall_total = None
+    fast_path = os.path.join(os.path.dirname(wasmref.lib_path()), "libwasm_stretch_fast.so")
+    if wasmref.available() and (not fast or os.path.exists(fast_path)):
         # native pthread pool, one reference instance per stream (oracle/ref_bench.c)
-        L = ctypes.CDLL(wasmref.lib_path())
-        L.refbench_run.restype = ctypes.c_double
-        L.refbench_run.argtypes = [ctypes.c_int] * 3 + [ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_float] + \
-            [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
-        chk = ctypes.c_double(0)
-        dt = L.refbench_run(threads, n_streams, CHANNELS, float(SR), 0, 0.0, 0.0, n_in_total, n_out_total, chunk,
-                            x.ctypes.data, ctypes.byref(chk))
-        kind, how = "reference", "native pthread pool over the reference's shipped binary (oracle/_ref, WASM->C, gcc -O2)"
+        L = ctypes.CDLL(fast_path if fast else wasmref.lib_path())
+        L.refbench_run2.restype = ctypes.c_double
+        L.refbench_run2.argtypes = [ctypes.c_int] * 3 + [ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_float] + \
+            [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        chk, proc = ctypes.c_double(0), ctypes.c_double(0)
+        wall_total = L.refbench_run2(threads, n_streams, CHANNELS, float(SR), 0, 0.0, 0.0, n_in_total, n_out_total, chunk,
+                                     x.ctypes.data, ctypes.byref(chk), ctypes.byref(proc))
+        dt = proc.value
+        kind = "reference"
+        how = "native pthread pool over the reference's shipped binary (oracle/_ref, WASM->C, gcc %s)" % \
+            ("-O3 -ffast-math -mavx2 -mfma" if fast else "-O2 -ffp-contract=off")
+    elif fast:
+        return None
     else:
         from concurrent.futures import ThreadPoolExecutor
 
@@ -215,26 +292,47 @@ def cpu_reference_run(n_streams, seconds_per_stream, threads):
         dt = time.perf_counter() - t0
         kind, how = "port", "oracle restatement (double-precision FFT) via ctypes threads"
     total = n_streams * CHANNELS * n_out_total
-    return {"value": total / dt, "unit": "samples/s", "cores": threads, "kind": kind,
-            "sample": "%d streams x %.1f s stereo 48 kHz presetDefault 0.8x, 480-sample calls, %d threads, %.1f s wall; %s"
+    return {"value": total / dt, "unit": "samples/s", "cores": threads, "per_core": total / dt / threads, "kind": kind,
+            "wall_s_process_only": dt, "wall_s_with_instance_creation": wall_total,
+            "sample": "%d streams x %.1f s stereo 48 kHz presetDefault 0.8x, 480-sample calls, %d threads, %.2f s inside process(); %s"
                       % (n_streams, seconds_per_stream, threads, dt, how)}
+
+
+def cpu_baseline_report(n_streams_per_thread, seconds_per_stream):
+    """cpu_baseline object of the JSON line: thread count = the CPUs this process may really use (affinity and cgroup
+    quota, not os.cpu_count()), per-core and aggregate figures, and the -O3 -ffast-math build beside the -O2 one."""
+    hc = host_cores()
+    threads = hc["usable"]
+    n = max(n_streams_per_thread * threads, 64)
+    r = cpu_reference_run(n, seconds_per_stream, threads)
+    r["host"] = hc
+    f = cpu_reference_run(n, seconds_per_stream, threads, fast=True)
+    if f:
+        r["fast_math_build"] = {"value": f["value"], "per_core": f["per_core"], "sample": f["sample"]}
+    return r
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    hc = host_cores()
+    threads = hc["usable"]
     vals, t_all = [], []
-    n_streams = max(threads * 8, 64)
+    n_streams = max(threads * 2, 64)
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        r = cpu_reference_run(n_streams, 2.0, threads)  # a bounded sample of the workload per step (~3.5 s of CPU work)
+        r = cpu_reference_run(n_streams, 10.0, threads)  # a bounded sample of the workload per step: 10 s of audio per stream
         if i >= args.warmup:
             vals.append(r["value"])
             t_all.append(time.perf_counter() - t0)
     v = float(np.mean(vals))
     w = workload(BATCH_PER_GPU)
     r["value"] = v
+    r["per_core"] = v / threads
+    r["host"] = hc
+    f = cpu_reference_run(n_streams, 10.0, threads, fast=True)
+    if f:
+        r["fast_math_build"] = {"value": f["value"], "per_core": f["per_core"], "sample": f["sample"]}
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(t_all)) * 1e3,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -313,6 +411,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU path (use --impl reference for the CPU baseline)")
     build_library()
+    orig_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local_rank)  # before the pinned host buffers are allocated (first touch)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -399,6 +499,8 @@ def main():
     e2e = {"value": tot_e / t_e, "unit": "samples/s",
            "h2d_bytes_per_step": int(x_pin[0].numel() * 4), "d2h_bytes_per_step": int(y_pin.numel() * 4),
            "ms_per_step": t_e / args.steps * 1e3,
+           "h2d_gbs_per_rank": x_pin[0].numel() * 4 / (t_e / args.steps) / 1e9, "d2h_gbs_per_rank": y_pin.numel() * 4 / (t_e / args.steps) / 1e9,
+           "numa": numa,
            "timed": "host wall clock around %d pipelined b200s_process_async() calls + synchronize, pinned H2D + D2H of every step inside" % args.steps,
            "sync_call": {"value": tot_s / t_s, "ms_per_step": t_s / args.steps * 1e3, "timed": "one blocking b200s_process() per step"}}
 
@@ -440,8 +542,8 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        cpu = cpu_reference_run(max(8 * threads, 64), 5.0, threads)
+        os.sched_setaffinity(0, orig_affinity)  # the CPU baseline uses every CPU of the lease, not only the GPU-local ones
+        cpu = cpu_baseline_report(2, 10.0)
 
     # the 16-bit PCM boundary (not the reference's float call: reported beside `e2e`, never instead of it), measured in a
     # child process so that nothing it does can take the line above with it

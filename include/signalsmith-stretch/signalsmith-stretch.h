@@ -14,13 +14,18 @@
 // the reference's Wav proxy of doubles, ... README.md:46); like the reference's copyInput()
 // (:220-226) the facade marshals element by element into planar float staging, then calls
 // b200s_process().  One object = a batch of one stream; use the C ABI (or `BatchStretch` below)
-// for batches.  Only Sample = float is GPU-backed.  Methods stay `void`; a CUDA failure is
-// reported through lastError() (the reference has no error path at all).  No CPU fallback.
+// for batches.  Only Sample = float is GPU-backed.  Methods stay `void` (the reference has no error path at all), so a
+// failure -- no usable GPU, an unsupported configuration, a CUDA error -- cannot be returned: it is FATAL.  The message
+// goes to stderr and the process aborts, because host code written against the reference has no reason to poll an error
+// flag and would otherwise write silence.  Define B200S_FACADE_SOFT_ERRORS before including this header to get the
+// sticky lastError() string instead (outputs are then zero-filled on failure).  No CPU fallback.
 #ifndef SIGNALSMITH_STRETCH_H
 #define SIGNALSMITH_STRETCH_H
 
 #include <cmath>
 #include <cstddef>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <string>
 #include <type_traits>
@@ -130,8 +135,15 @@ private:
 	std::vector<float> stageIn, stageOut;
 	std::string error;
 
+	bool failed = false; // soft-error mode: the last call failed, scatter() writes zeros
 	void check(int rc) {
-		if (rc != 0) error = engine ? b200s_last_error(engine) : b200s_last_error(nullptr);
+		failed = rc != 0;
+		if (!failed) return;
+		error = engine ? b200s_last_error(engine) : b200s_last_error(nullptr);
+#ifndef B200S_FACADE_SOFT_ERRORS
+		std::fprintf(stderr, "signalsmith-stretch (B200): fatal: %s (code %d)\n", error.c_str(), rc);
+		std::abort();
+#endif
 	}
 	template <class Inputs>
 	void gather(Inputs &&inputs, int offset, int n) {
@@ -145,7 +157,7 @@ private:
 	void scatter(Outputs &&outputs, int n) {
 		for (int c = 0; c < channels; ++c) {
 			auto &&channel = outputs[c];
-			for (int i = 0; i < n; ++i) channel[i] = stageOut[size_t(c) * n + i];
+			for (int i = 0; i < n; ++i) channel[i] = failed ? 0.f : stageOut[size_t(c) * n + i];
 		}
 	}
 };

@@ -31,15 +31,28 @@ typedef struct {
 	int next;
 	pthread_mutex_t mu;
 	double checksum;
+	double procMax; /* largest per-thread sum of the time spent inside the process() loops (instance set-up excluded) */
 } Job;
+
+static double now_s(void) {
+	struct timespec t;
+	clock_gettime(CLOCK_MONOTONIC, &t);
+	return t.tv_sec + 1e-9 * t.tv_nsec;
+}
 
 static void *worker(void *arg) {
 	Job *j = (Job *)arg;
+	double proc = 0;
 	for (;;) {
 		pthread_mutex_lock(&j->mu);
 		int s = j->next++;
 		pthread_mutex_unlock(&j->mu);
-		if (s >= j->streams) break;
+		if (s >= j->streams) {
+			pthread_mutex_lock(&j->mu);
+			if (proc > j->procMax) j->procMax = proc;
+			pthread_mutex_unlock(&j->mu);
+			break;
+		}
 		W *w = wasm_new();
 		wasm_export_f(w);
 		wasm_export_y(w, 0, 0);
@@ -52,6 +65,7 @@ static void *worker(void *arg) {
 		uint32_t ptr = wasm_export_h(w, j->channels, len);
 		int i = 0, done = 0;
 		double acc = 0;
+		const double tp0 = now_s(); /* timed: the process() calls only, not the instance creation / preset above */
 		while (done < j->nOut) {
 			int co = j->chunkOut < j->nOut - done ? j->chunkOut : j->nOut - done;
 			int ci = (int)((double)(done + co) * ratio + 0.5) - i;
@@ -65,6 +79,7 @@ static void *worker(void *arg) {
 			i += ci;
 			done += co;
 		}
+		proc += now_s() - tp0;
 		pthread_mutex_lock(&j->mu);
 		j->checksum += acc;
 		pthread_mutex_unlock(&j->mu);
@@ -73,9 +88,11 @@ static void *worker(void *arg) {
 	return 0;
 }
 
-/* returns wall seconds; *checksum receives a data-dependent value so the work cannot be elided */
-double refbench_run(int threads, int streams, int channels, float sr, int preset, float semitones, float tonality,
-                    int nIn, int nOut, int chunkOut, const float *x, double *checksum) {
+/* returns wall seconds (instance creation included); *checksum receives a data-dependent value so the work cannot be
+ * elided; *procSeconds (may be null) receives the wall time of the process() calls alone: the largest per-thread sum of
+ * the intervals spent inside the process() loops, i.e. what the pool would take if instances were created beforehand */
+double refbench_run2(int threads, int streams, int channels, float sr, int preset, float semitones, float tonality,
+                     int nIn, int nOut, int chunkOut, const float *x, double *checksum, double *procSeconds) {
 	Job j;
 	memset(&j, 0, sizeof j);
 	j.streams = streams; j.channels = channels; j.preset = preset; j.nIn = nIn; j.nOut = nOut; j.chunkOut = chunkOut;
@@ -89,5 +106,11 @@ double refbench_run(int threads, int streams, int channels, float sr, int preset
 	for (int t = 0; t < threads; ++t) pthread_join(th[t], 0);
 	clock_gettime(CLOCK_MONOTONIC, &t1);
 	if (checksum) *checksum = j.checksum;
+	if (procSeconds) *procSeconds = j.procMax;
 	return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+double refbench_run(int threads, int streams, int channels, float sr, int preset, float semitones, float tonality,
+                    int nIn, int nOut, int chunkOut, const float *x, double *checksum) {
+	return refbench_run2(threads, streams, channels, sr, preset, semitones, tonality, nIn, nOut, chunkOut, x, checksum, 0);
 }

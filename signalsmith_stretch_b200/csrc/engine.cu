@@ -43,6 +43,7 @@ struct b200s_engine {
 	cudaStream_t subStream[kMaxSub] = {};
 	cudaEvent_t evBegin = 0, evSubDone[kMaxSub] = {};
 	int chainedGroups = 0; // > 0: the last operation was a host-buffer process() over this many stream groups (see process_impl)
+	int chainedIn = -1, chainedOut = -1; // its per-channel sample counts: the groups' slabs of the staging buffers sit at sBase*C*n
 	int chainV = 0, fftV1 = 0; // b200s_set_tuning overrides (0 = default)
 	int exactMath = 0;         // b200s_set_tuning key 3: 1 = the phase chain in the reference's unfused IEEE arithmetic
 	int nHostParts = 12; // (measured, batch 1024 stereo: 2 -> 15.1, 4 -> 13.0, 8 -> 12.2, 12 -> 11.2, 16 -> 11.8 ms per step) host-buffer API: stream groups whose H2D copy / kernels / D2H copy are pipelined
@@ -69,7 +70,7 @@ struct b200s_engine {
 	float *dStPredE = 0;
 	float4 *dStIl = 0;
 	// call scratch
-	int maxFrames = 0;
+	int maxFrames = 0, coefFrames = 0; // coefFrames: block capacity of the coefficient rows (mapped / formant calls only)
 	Frame *dFrames = 0;
 	Call *dCall = 0;
 	Job *dJobs = 0;
@@ -126,7 +127,7 @@ static void free_all(b200s_engine *e) {
 	dfree(e->dFrames); dfree(e->dCall); dfree(e->dJobs); dfree(e->dSpec); dfree(e->dY); dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dE); dfree(e->dStPitch); dfree(e->dPitch);
 	dfree(e->dIn); dfree(e->dOut); dfree(e->dZero); dfree(e->dTmp); dfree(e->dIn16); dfree(e->dOut16);
 	e->in16Cap = e->out16Cap = 0;
-	e->maxFrames = 0;
+	e->maxFrames = e->coefFrames = 0;
 	e->inCap = e->outCap = e->zeroCap = e->tmpCap = 0;
 }
 
@@ -486,13 +487,31 @@ static int ensure_scratch(b200s_engine *e, int nOut) {
 	if ((rc = dalloc(e, &e->dJobs, (size_t)g.S * need * 2 * g.C))) return rc;
 	if ((rc = dalloc(e, &e->dSpec, 2 * n))) return rc;
 	if ((rc = dalloc(e, &e->dY, n))) return rc;
+	if ((rc = dalloc(e, &e->dE, n))) return rc; // Prediction::energy rows: also the state carry of the generic direct chains
+	if ((rc = dalloc(e, &e->dPitch, (size_t)g.S * need))) return rc;
+	e->maxFrames = need;
+	// the complex coefficient rows follow maxFrames (their row offsets use it) but only exist once a call needed them
+	dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2);
+	e->coefFrames = 0;
+	return 0;
+}
+// Complex coefficient rows of k_prep (32 B per bin-channel and block: 6.6 GB at batch 1024 x 33 blocks stereo): only calls
+// with a frequency map or formant processing launch k_prep, so only they pay for them (b200s_reserve() allocates them
+// when the parameters set at that time need them).
+static bool params_plain(const b200s_engine *e) {
+	return !(e->prm.mapN > 0 || e->prm.freqMultiplier != 1.0f) && e->prm.formantMultiplier == 1.0f;
+}
+static int ensure_coef(b200s_engine *e) {
+	if (e->coefFrames == e->maxFrames && e->dPI) return 0;
+	const Cfg &g = e->cfg;
+	CK(cudaStreamSynchronize(e->stream));
+	const size_t n = (size_t)g.S * e->maxFrames * g.C * g.K;
+	int rc;
 	if ((rc = dalloc(e, &e->dPI, n))) return rc;
 	if ((rc = dalloc(e, &e->dFT, n))) return rc;
 	if ((rc = dalloc(e, &e->dT1, n))) return rc;
 	if ((rc = dalloc(e, &e->dT2, n))) return rc;
-	if ((rc = dalloc(e, &e->dE, n))) return rc;
-	if ((rc = dalloc(e, &e->dPitch, (size_t)g.S * need))) return rc;
-	e->maxFrames = need;
+	e->coefFrames = e->maxFrames;
 	return 0;
 }
 static int ensure_buf(b200s_engine *e, float **p, size_t *cap, size_t n, bool zero) {
@@ -519,6 +538,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	}
 	int rc;
 	if ((rc = ensure_scratch(e, nOut))) return rc;
+	if (!params_plain(e) && (rc = ensure_coef(e))) return rc;
 	Ctx x = make_ctx(e);
 	x.in = dIn; x.out = dOut; x.nIn = nIn; x.nOut = nOut;
 	x.inChanStride = inChanStride; x.inStreamStride = inStreamStride;
@@ -538,10 +558,16 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	// kernels are ordered on the group's own stream and touch only that group's streams of the state, so group g of
 	// call n+1 may start its H2D copy while other groups still finish call n (b200s_process_async pipelines calls this
 	// way).  Anything else first joins: the main stream has waited for every group at the end of the previous call.
-	const bool chained = hostIO && nSub > 1 && e->chainedGroups == nSub;
+	// The groups' slabs of the shared staging buffers sit at sBase*C*nIn / sBase*C*nOut, so they only coincide from call to
+	// call when the sample counts do: a call with different counts must first join (otherwise group g's copy of call n+1
+	// could overwrite the slab a neighbouring group still uses for call n); evBegin below is that join, since the main
+	// stream has waited for every group's evSubDone at the end of the previous call.
+	const bool chained = hostIO && nSub > 1 && e->chainedGroups == nSub && e->chainedIn == nIn && e->chainedOut == nOut;
 	e->chainedGroups = (hostIO && nSub > 1) ? nSub : 0;
+	e->chainedIn = nIn;
+	e->chainedOut = nOut;
 	if (nSub > 1 && !chained) CK(cudaEventRecord(e->evBegin, e->stream));
-	const bool plain = !(e->prm.mapN > 0 || e->prm.freqMultiplier != 1.0f) && e->prm.formantMultiplier == 1.0f;
+	const bool plain = params_plain(e);
 	const bool formantsOn = e->prm.formantMultiplier != 1.0f || (e->prm.formantCompensation && (e->prm.mapN > 0 || e->prm.freqMultiplier != 1.0f)); // :310
 	const int chainV = chain_version(g, e->chainV, e->fftV1);
 	const bool pairFft = use_pair_fft(g, e->fftV1);
@@ -808,6 +834,7 @@ int b200s_reserve(b200s_engine *e, int maxIn, int maxOut) {
 	NEED_CFG();
 	int rc;
 	if ((rc = ensure_scratch(e, maxOut))) return rc;
+	if (!params_plain(e) && (rc = ensure_coef(e))) return rc;
 	if ((rc = stage_in(e, 0, 0))) return rc;
 	size_t ci = (size_t)e->cfg.S * e->cfg.C * std::max(maxIn, 1), co = (size_t)e->cfg.S * e->cfg.C * std::max(maxOut, 1);
 	if ((rc = ensure_buf(e, &e->dIn, &e->inCap, ci, false))) return rc;
@@ -870,8 +897,6 @@ int b200s_set_freq_map_table(b200s_engine *e, const float *fin, const float *fou
 	return 0;
 }
 
-static int check_formant_support(b200s_engine *) { return 0; } // automatic pitch detection (setFormantBase(0)) runs on the GPU: k_pitch
-
 int b200s_seek_device(b200s_engine *e, const float *dIn, int n, double rate) {
 	NEED_CFG();
 	if (n < 0) return B200S_EINVAL;
@@ -880,7 +905,6 @@ int b200s_seek_device(b200s_engine *e, const float *dIn, int n, double rate) {
 int b200s_process_device(b200s_engine *e, const float *dIn, int nIn, float *dOut, int nOut) {
 	NEED_CFG();
 	int rc;
-	if ((rc = check_formant_support(e))) return rc;
 	return process_impl(e, dIn, nIn, (long long)e->cfg.C * nIn, nIn, dOut, nOut, (long long)e->cfg.C * nOut, nOut);
 }
 int b200s_flush_device(b200s_engine *e, float *dOut, int nOut, float rate) {
@@ -900,7 +924,6 @@ int b200s_seek(b200s_engine *e, const float *in, int n, double rate) {
 int b200s_process(b200s_engine *e, const float *in, int nIn, float *out, int nOut) {
 	NEED_CFG();
 	int rc;
-	if ((rc = check_formant_support(e))) return rc;
 	if ((rc = stage_in(e, nullptr, nIn))) return rc; // capacity only: the copies are issued per stream group
 	if ((rc = stage_out(e, nOut))) return rc;
 	if ((rc = process_impl(e, e->dIn, nIn, (long long)e->cfg.C * nIn, nIn, e->dOut, nOut, (long long)e->cfg.C * nOut, nOut, in, out))) return rc;
@@ -930,7 +953,6 @@ int b200s_process_pcm16(b200s_engine *e, const short *in, int nIn, short *out, i
 int b200s_process_async(b200s_engine *e, const float *in, int nIn, float *out, int nOut) {
 	NEED_CFG();
 	int rc;
-	if ((rc = check_formant_support(e))) return rc;
 	if ((size_t)e->cfg.S * e->cfg.C * std::max(nIn, 1) > e->inCap || (size_t)e->cfg.S * e->cfg.C * std::max(nOut, 1) > e->outCap || !e->dIn || !e->dOut) {
 		// growing the staging buffers would invalidate copies still in flight: drain first
 		CK(cudaStreamSynchronize(e->stream));
@@ -951,7 +973,6 @@ int b200s_output_seek(b200s_engine *e, const float *in, int inputLength) {
 	NEED_CFG();
 	if (inputLength < 0) return B200S_EINVAL;
 	int rc;
-	if ((rc = check_formant_support(e))) return rc;
 	if ((rc = stage_in(e, in, inputLength))) return rc;
 	if ((rc = output_seek_impl(e, e->dIn, inputLength, (long long)e->cfg.C * inputLength, inputLength))) return rc;
 	CK(cudaStreamSynchronize(e->stream));
@@ -961,7 +982,6 @@ int b200s_exact(b200s_engine *e, const float *in, int nIn, float *out, int nOut,
 	NEED_CFG();
 	if (nIn < 0 || nOut <= 0) return B200S_EINVAL;
 	int rc;
-	if ((rc = check_formant_support(e))) return rc;
 	const Cfg &g = e->cfg;
 	float playbackRate = nIn / float(nOut);
 	int seekLen = b200s_output_seek_length(e, playbackRate);

@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(256, 2) k_analyse2(Ctx x) {
 			const int shA = x.inAligned ? (cur.a.start & 3) : 0, shB = x.inAligned ? (cur.b.start & 3) : 0;
 			if (tid == 0) {
 				float *xw = (float *)buf;
-				// interleaved mode: transform into scratch rows (cPI is unused on the direct path), then interleave
-				float2 *tA = x.specIl ? x.cPI + coef_off(x, cur.s, 0, 0) : dstA, *tB = x.specIl ? tA + KT : dstB;
+				// interleaved mode: transform into scratch rows (the Y rows of block 0: the chain writes them only later), then interleave
+				float2 *tA = x.specIl ? x.Y + coef_off(x, cur.s, 0, 0) : dstA, *tB = x.specIl ? tA + KT : dstB;
 				for (int i = 0; i < B; ++i) xw[i] = fmul(stA[i + shA], x.window[i]);
 				emu_exact_forward(xw, B, o, 2 * KT, tA);
 				if (cur.hasB) {
@@ -468,7 +468,8 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 			}
 		}
 		if (hasB) {
-			// gap <= P always here?  blocks trigger every H <= B <= P samples; larger gaps cannot occur inside a call
+			// gap <= P: inside a call k_plan triggers block f+1 exactly H output samples after block f (samplesSinceLast
+			// restarts at 0 on a trigger and a block fires the moment it reaches H, :281-286), and H <= B <= P (configure)
 			head = (head + gap) % P;
 			emitted += gap;
 		}
