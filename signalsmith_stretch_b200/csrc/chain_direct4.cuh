@@ -97,6 +97,15 @@ struct Chain4Tiles {
 	const float4 *rowIn[32], *rowPv[32];
 };
 
+// true when k_chain_ws (chain_ws.cuh) takes this stream: every block's time factor is within the reach of its 16-bin
+// spectrum ring (timeFactor <= 2, the clean-stretch limit of :509).  Evaluated identically by both kernels.
+__device__ __forceinline__ bool ws_stream_ok(const Ctx &x, int s, int nFrames, int lane) {
+	bool bad = false;
+	for (int f = lane; f < nFrames; f += 32)
+		bad = bad || !(fmaxf(x.frames[(size_t)s * x.maxFrames + f].timeFactor, 1.0f / B200S_MAX_CLEAN_STRETCH) <= B200S_MAX_CLEAN_STRETCH);
+	return !__any_sync(0xffffffffu, bad);
+}
+
 template <int LT, bool FAST>
 __global__ void __launch_bounds__(32) k_chain_direct4(Ctx x) {
 	const Cfg &g = x.cfg;
@@ -106,6 +115,7 @@ __global__ void __launch_bounds__(32) k_chain_direct4(Ctx x) {
 	const int s = x.sBase + blockIdx.x;
 	const Call cl = x.call[s];
 	if (cl.nFrames == 0) return;
+	if (x.wsRan && ws_stream_ok(x, s, cl.nFrames, lane)) return; // k_chain_ws has done this stream
 	constexpr int G = LT + 2; // lane skew in bins
 	constexpr int NF = LT + 1; // FIFO entries: bins b .. b+L of the lane's block
 	Chain4Tiles &U = *(Chain4Tiles *)dyn_smem;

@@ -24,6 +24,7 @@
 #include "stft2.cuh"
 #include "chain_direct3.cuh"
 #include "chain_direct4.cuh"
+#include "chain_ws.cuh"
 
 using namespace b200s;
 
@@ -248,9 +249,20 @@ static int chain_version(const Cfg &g, int override, int forceFftV1) {
 		const char *v = getenv("B200S_CHAIN_V");
 		env = v ? atoi(v) : 0;
 	}
-	int want = override ? override : env ? env : 4;
+	int want = override ? override : env ? env : 5;
 	if (want >= 3 && !(g.C == 2 && use_pair_fft(g, forceFftV1))) want = 2;
+	if (want == 5 && g.L > 4) want = 4; // k_chain_ws is laid out for L <= 4 (both presets)
 	return want;
+}
+// 5 = warp-specialised producer / consumer chain (chain_ws.cuh), followed by k_chain_direct4 for the streams it leaves
+template <bool FAST>
+static ChainKernel chain_ws_kernel(int L) {
+	switch (L) {
+	case 1: return k_chain_ws<1, FAST>;
+	case 2: return k_chain_ws<2, FAST>;
+	case 3: return k_chain_ws<3, FAST>;
+	default: return k_chain_ws<4, FAST>;
+	}
 }
 template <bool FAST>
 static ChainKernel chain4_kernel(int L) {
@@ -266,7 +278,7 @@ static ChainKernel chain4_kernel(int L) {
 	}
 }
 static ChainKernel chain3_kernel(const Cfg &g, int v, bool fast) {
-	if (v == 4) return fast ? chain4_kernel<true>(g.L) : chain4_kernel<false>(g.L);
+	if (v >= 4) return fast ? chain4_kernel<true>(g.L) : chain4_kernel<false>(g.L);
 	switch (g.L) {
 	case 1: return k_chain_direct3<1>;
 	case 2: return k_chain_direct3<2>;
@@ -461,6 +473,10 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	CK(cudaFuncSetAttribute(chain_kernel(g, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, false)));
 	CK(cudaFuncSetAttribute(chain_kernel(g, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, true)));
 	CK(cudaFuncSetAttribute(chain2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain2(g.C, CH2_MAXW)));
+	if (g.L <= 4) { // seven two-warp CTAs of 30.6 KB per SM: ask for the full shared-memory carve-out
+		CK(cudaFuncSetAttribute(chain_ws_kernel<true>(g.L), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+		CK(cudaFuncSetAttribute(chain_ws_kernel<false>(g.L), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+	}
 	if (use_pair_fft(g)) {
 		CK(cudaFuncSetAttribute(analyse2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_analyse2(g)));
 		CK(cudaFuncSetAttribute(synth2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_synth2(g)));
@@ -604,7 +620,19 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 					CKL();
 				}
 				if (!plain) PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g, formantsOn), st, x));
-				if (plain && chainV >= 3) {
+				if (plain && chainV == 5) {
+					int _rc;
+					if ((_rc = prof_mark(e, PK_CHAIN, true))) return _rc;
+					const bool fast = !e->exactMath;
+					ChainKernel kw = fast ? chain_ws_kernel<true>(g.L) : chain_ws_kernel<false>(g.L), k4 = chain3_kernel(g, 4, fast);
+					B200S_LAUNCH(kw, dim3(x.sCount), dim3(64), fast ? smem_chain_ws<true>() : smem_chain_ws<false>(), st, x);
+					CKL();
+					x.wsRan = 1; // streams with a block beyond the 2x stretch limit: k_chain_direct4 (every other CTA exits at once)
+					B200S_LAUNCH(k4, dim3(x.sCount), dim3(32), smem_chain4(g.L), st, x);
+					CKL();
+					x.wsRan = 0;
+					if ((_rc = prof_mark(e, PK_CHAIN, false))) return _rc;
+				} else if (plain && chainV >= 3) {
 					PROF(PK_CHAIN, B200S_LAUNCH(chain3_kernel(g, chainV, !e->exactMath), dim3(x.sCount), dim3(32), chainV == 4 ? smem_chain4(g.L) : sizeof(Chain3Tiles), st, x));
 				} else if (plain && chainV == 2) {
 					const int W = chain2_warps(g, nOut);
@@ -803,7 +831,7 @@ int b200s_set_sub_batches(b200s_engine *e, int n) {
 }
 int b200s_set_tuning(b200s_engine *e, int key, int value) {
 	if (!e) return B200S_EINVAL;
-	if (key == 0 && value >= 0 && value <= 4) e->chainV = value;
+	if (key == 0 && value >= 0 && value <= 5) e->chainV = value;
 	else if (key == 1 && (value == 0 || value == 1)) e->fftV1 = value;
 	else if (key == 2 && value >= 1) e->nHostParts = std::min(value, (int)b200s_engine::kMaxSub);
 	else if (key == 3 && (value == 0 || value == 1)) e->exactMath = value;
