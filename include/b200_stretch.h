@@ -122,6 +122,10 @@ int b200s_timer_start(b200s_engine *e);
 int b200s_timer_stop(b200s_engine *e, float *milliseconds); /* synchronises on the stop event */
 /* Kernels launched by this handle since creation (claim for bench.py's "gpu_launches"). */
 long long b200s_kernel_launches(const b200s_engine *e);
+/* Device allocations (cudaMalloc calls) made by this handle since creation.  The reference asserts "no allocation in
+ * process()" (cmd/main-dev.cpp:158-163); the equivalent here: after b200s_reserve() with the largest call sizes (and
+ * with the parameters already set), process() leaves this count unchanged (tests/test_gpu_parity.py). */
+long long b200s_device_allocations(const b200s_engine *e);
 /* Per-kernel device time of process(): between begin and end every kernel of the process()
  * launch sequence is bracketed by CUDA events on the handle's stream.  `ms`/`counts` receive, in
  * this order: plan, analyse, prep, chain, synth, commit (n >= 6). */

@@ -46,7 +46,7 @@ def _lib(kind):
         "output_seek_length": (ci, [vp, cf]), "bands": (ci, [vp]), "fft_samples": (ci, [vp]),
         "set_transpose_factor": (None, [vp, cf, cf]), "set_transpose_semitones": (None, [vp, cf, cf]),
         "set_formant_factor": (None, [vp, cf, ci]), "set_formant_semitones": (None, [vp, cf, ci]),
-        "set_formant_base": (None, [vp, cf]), "set_freq_map_quadratic": (None, [vp, cf, cf]),
+        "set_formant_base": (None, [vp, cf]), "set_freq_map_quadratic": (None, [vp, cf, cf]), "set_freq_map_table": (None, [vp, fp, fp, ci]),
         "seek": (None, [vp, fp, ci, cd]), "output_seek": (None, [vp, fp, ci]),
         "process": (None, [vp, fp, ci, fp, ci]), "flush": (None, [vp, fp, ci, cf]),
         "exact": (ci, [vp, fp, ci, fp, ci]),
@@ -138,6 +138,12 @@ class CpuStretch:
 
     def setFreqMapQuadratic(self, a, b):
         self.f["set_freq_map_quadratic"](self.h, a, b)
+
+    def setFreqMapTable(self, fin, fout):
+        """setFreqMap with a piecewise-linear function given by its break points (freq as a multiple of the sample rate)."""
+        fin = np.ascontiguousarray(fin, np.float32)
+        fout = np.ascontiguousarray(fout, np.float32)
+        self.f["set_freq_map_table"](self.h, _fp(fin), _fp(fout), len(fin))
 
     def _in(self, x):
         x = np.ascontiguousarray(np.asarray(x, np.float32).reshape(self.channels, -1))

@@ -62,6 +62,26 @@ void hdr_set_formant_base(void *h, float f) { ((Stretch *)h)->setFormantBase(f);
 void hdr_set_freq_map_quadratic(void *h, float a, float b) {
 	((Stretch *)h)->setFreqMap([a, b](float f) { return a * f + b * f * f; });
 }
+// custom map kind 2: piecewise-linear table (same function as oracle/stretch_oracle.cpp pwl_map and the product's map_freq)
+static inline float pwl_map(const float *in, const float *out, int n, float freq) {
+	if (n == 1) return out[0] + (freq - in[0]);
+	int lo = 0, hi = n - 1;
+	while (hi - lo > 1) {
+		int mid = (lo + hi) >> 1;
+		if (in[mid] <= freq) lo = mid;
+		else hi = mid;
+	}
+	float x0 = in[lo], x1 = in[lo + 1], y0 = out[lo], y1 = out[lo + 1];
+	return y0 + (freq - x0) * ((y1 - y0) / (x1 - x0));
+}
+void hdr_set_freq_map_table(void *h, const float *fin, const float *fout, int n) {
+	if (n <= 0) {
+		((Stretch *)h)->setFreqMap(nullptr);
+		return;
+	}
+	std::vector<float> a(fin, fin + n), b(fout, fout + n);
+	((Stretch *)h)->setFreqMap([a, b](float f) { return pwl_map(a.data(), b.data(), (int)a.size(), f); });
+}
 void hdr_seek(void *h, const float *in, int n, double rate) {
 	ConstPlanar p{in, n};
 	((Stretch *)h)->seek(p, n, rate);

@@ -53,6 +53,22 @@ struct Frame {
 	float timeFactor;
 };
 
+// custom map kind 2: a piecewise-linear table, i.e. what a caller passes to setFreqMap (:120) when the map is tabulated:
+// `n` points (in[i] ascending), linear between neighbours and extrapolated beyond the ends.  The same float expression,
+// segment search and operation order as the product's map_freq (csrc/kernels.cuh) -- it is the USER's function, so the
+// reference, the oracle and the product must all be handed the identical one.
+static inline float pwl_map(const float *in, const float *out, int n, float freq) {
+	if (n == 1) return out[0] + (freq - in[0]);
+	int lo = 0, hi = n - 1;
+	while (hi - lo > 1) {
+		int mid = (lo + hi) >> 1;
+		if (in[mid] <= freq) lo = mid;
+		else hi = mid;
+	}
+	float x0 = in[lo], x1 = in[lo + 1], y0 = out[lo], y1 = out[lo + 1];
+	return y0 + (freq - x0) * ((y1 - y0) / (x1 - x0));
+}
+
 struct Stretch {
 	// ---------------- configuration (signalsmith-stretch.h:63-94, dependency contract App. B) ----
 	int C = 0, B = 0, H = 0, N = 0, K = 0;
@@ -67,7 +83,8 @@ struct Stretch {
 	bool formantCompensation = false;
 	float formantMultiplier = 1, invFormantMultiplier = 1;
 	float formantBaseFreq = 0;
-	int customMap = 0; // 0 none, 1 quadratic a*f+b*f*f (test stand-in for setFreqMap, :120)
+	int customMap = 0; // 0 none, 1 quadratic a*f+b*f*f (test stand-in for setFreqMap, :120), 2 piecewise-linear table
+	std::vector<float> mapTabIn, mapTabOut;
 	float mapA = 1, mapB = 0;
 
 	// ---------------- scheduler state (:494-529) ----------------
@@ -340,6 +357,7 @@ struct Stretch {
 	// :850-856
 	float mapFreq(float freq) const {
 		if (customMap == 1) return mapA * freq + mapB * freq * freq;
+		if (customMap == 2) return pwl_map(mapTabIn.data(), mapTabOut.data(), (int)mapTabIn.size(), freq);
 		if (freq > freqTonalityLimit) return freq + (freqMultiplier - 1) * freqTonalityLimit;
 		return freq * freqMultiplier;
 	}
@@ -800,6 +818,12 @@ void orc_set_freq_map_quadratic(void *h, float a, float b) {
 	s.customMap = 1;
 	s.mapA = a;
 	s.mapB = b;
+}
+void orc_set_freq_map_table(void *h, const float *fin, const float *fout, int n) {
+	Stretch &s = *(Stretch *)h;
+	s.customMap = n > 0 ? 2 : 0;
+	s.mapTabIn.assign(fin, fin + n);
+	s.mapTabOut.assign(fout, fout + n);
 }
 void orc_seek(void *h, const float *in, int n, double rate) { ((Stretch *)h)->seek(in, n, rate); }
 void orc_output_seek(void *h, const float *in, int n) { ((Stretch *)h)->outputSeek(in, n, n); }

@@ -104,15 +104,15 @@ __global__ void __launch_bounds__(64, 7) k_chain_ws(Ctx x) {
 			const float2 rotS = rotOn ? x.rotStep : make_float2(1.f, 0.f);
 			const int fI = lane & 3, fF = lane >> 2; // fill / write-back: lane -> (bin offset, row within a group of 8): a quarter-warp covers 64 B of two rows
 			__syncwarp();
+			const float4 *rIn[4], *rPv[4]; // the four rows this lane copies from, for the whole group
+#pragma unroll
+			for (int it = 0; it < 4; ++it) {
+				rIn[it] = U.rowIn[fF + 8 * it];
+				rPv[it] = U.rowPv[fF + 8 * it];
+			}
 			// asynchronous fill of chunk n: 4 new bins per block, both channels per 16-byte copy
 			auto fill = [&](int n) {
 				const int kf = n * WS_CH, buf = n & 1;
-				const float4 *rIn[4], *rPv[4];
-#pragma unroll
-				for (int it = 0; it < 4; ++it) {
-					rIn[it] = U.rowIn[fF + 8 * it];
-					rPv[it] = U.rowPv[fF + 8 * it];
-				}
 #pragma unroll
 				for (int it = 0; it < 4; ++it) {
 					const int fl = fF + 8 * it;
@@ -136,15 +136,18 @@ __global__ void __launch_bounds__(64, 7) k_chain_ws(Ctx x) {
 				}
 			};
 			// the tiles of chunk n (its raw spectra are complete and visible)
-			auto produce = [&](int n) {
+			// INTERIOR (about nine chunks in ten of a full group): every lane is active and all its bins and interpolation
+			// points lie inside [L, K) for the whole chunk, so every mask below is an identity and is compiled out
+			auto produce = [&](int n, auto intTag) {
+				constexpr bool INTERIOR = decltype(intTag)::value;
 				const int nb = n & 1;
 #pragma unroll
 				for (int i = 0; i < WS_CH; ++i) {
 					const int q = n * WS_CH + i - WS_G * lane; // bin of the preliminary prediction
 					const int b = q - WS_D, q1 = b + 1;        // final bin of the same step; bin of the short twist
-					const bool qIn = active && (unsigned)q < (unsigned)K;
-					const bool q1In = active && q1 > 0 && q1 < K; // the short twist of bin 0 is never used (b > 0, :748)
-					const bool bIn = active && (unsigned)b < (unsigned)K;
+					const bool qIn = INTERIOR || (active && (unsigned)q < (unsigned)K);
+					const bool q1In = INTERIOR || (active && q1 > 0 && q1 < K); // the short twist of bin 0 is never used (b > 0, :748)
+					const bool bIn = INTERIOR || (active && (unsigned)b < (unsigned)K);
 					const float i2 = fsub((float)q, longTf); // :757
 					const int l2 = (int)floorf(i2);
 					const float f2s = fsub(i2, (float)l2);
@@ -154,10 +157,10 @@ __global__ void __launch_bounds__(64, 7) k_chain_ws(Ctx x) {
 					const c2 inq = ld_c2s(&U.in[q & (WS_RING - 1)][lane]);
 					const c2 pv = ld_c2s(&U.pv[nb][i][lane]);
 					const c2 in1 = ld_c2s(&U.in[q1 & (WS_RING - 1)][lane]);
-					const c2 lo2 = sel_c2(l2 >= 0, ld_c2s(&U.in[l2 & (WS_RING - 1)][lane]));
-					const c2 hi2 = sel_c2(l2 >= -1, ld_c2s(&U.in[(l2 + 1) & (WS_RING - 1)][lane]));
-					const c2 lo1 = sel_c2(l1 >= 0, ld_c2s(&U.in[l1 & (WS_RING - 1)][lane]));
-					const c2 hi1 = sel_c2(l1 >= -1, ld_c2s(&U.in[(l1 + 1) & (WS_RING - 1)][lane]));
+					const c2 lo2 = sel_c2(INTERIOR || l2 >= 0, ld_c2s(&U.in[l2 & (WS_RING - 1)][lane]));
+					const c2 hi2 = sel_c2(INTERIOR || l2 >= -1, ld_c2s(&U.in[(l2 + 1) & (WS_RING - 1)][lane]));
+					const c2 lo1 = sel_c2(INTERIOR || l1 >= 0, ld_c2s(&U.in[l1 & (WS_RING - 1)][lane]));
+					const c2 hi1 = sel_c2(INTERIOR || l1 >= -1, ld_c2s(&U.in[(l1 + 1) & (WS_RING - 1)][lane]));
 					// the previous block's Prediction::energy at bin q (:707): |its input|^2 on this path; lane 0: state / predecessor row
 					f2 re;
 					{
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(64, 7) k_chain_ws(Ctx x) {
 					const float2 rot = rotq;
 					{
 						const float2 rn = xmul(rotq, rotS); // the table recurrence stays in the reference's own arithmetic
-						rotq = make_float2(q >= 0 ? rn.x : rotq.x, q >= 0 ? rn.y : rotq.y);
+						rotq = make_float2((INTERIOR || q >= 0) ? rn.x : rotq.x, (INTERIOR || q >= 0) ? rn.y : rotq.y);
 					}
 					c2 a, t1, t2;
 					if constexpr (FAST) {
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(64, 7) k_chain_ws(Ctx x) {
 					const c2 pB = sel_c2(bIn, c2{f2_make(l1 == b ? f2_lo(lo1.re) : f2_lo(hi1.re), l1 == b ? f2_hi(lo1.re) : f2_hi(hi1.re)),
 					                              f2_make(l1 == b ? f2_lo(lo1.im) : f2_lo(hi1.im), l1 == b ? f2_hi(lo1.im) : f2_hi(hi1.im))});
 					U.A[nb][i][lane] = pack_c2(sel_c2(qIn, a));
-					U.T2[nb][i][lane] = pack_c2(sel_c2(qIn && q >= LT, t2)); // used at b = q (b >= L, :755) and at b = q - L (b < K - L, :776)
+					U.T2[nb][i][lane] = pack_c2(sel_c2(INTERIOR || (qIn && q >= LT), t2)); // used at b = q (b >= L, :755) and at b = q - L (b < K - L, :776)
 					U.T1[nb][i][lane] = pack_c2(sel_c2(q1In, t1));           // used at b = q1 (b > 0) and at b = q1 - 1 (b < K - 1, :766)
 					U.P[nb][i][lane] = pack_c2(pB);
 				}
@@ -217,11 +220,17 @@ __global__ void __launch_bounds__(64, 7) k_chain_ws(Ctx x) {
 					}
 				}
 			};
+			// chunks [intFrom, intTo): lane 31's interpolation points (down to q - 8 - 1) and final bin are >= L, lane 0's q < K
+			const int intFrom = nAct == 32 ? (WS_G * 31 + 16 + WS_CH - 1) / WS_CH : nChunks, intTo = (K - WS_CH + 1) / WS_CH;
+			auto produce_any = [&](int n) {
+				if (n >= intFrom && n < intTo) produce(n, std::true_type{});
+				else produce(n, std::false_type{});
+			};
 			fill(0);
 			if (nChunks > 1) fill(1);
 			cp_async_wait_all();
 			__syncwarp();
-			produce(0);
+			produce_any(0);
 			for (int n = 0; n < nChunks; ++n) {
 				__syncthreads(); // tiles of chunk n complete; the consumer is done with chunk n-1
 				cp_async_wait_all(); // raw spectra of chunk n+1 (issued one iteration ago)
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(64, 7) k_chain_ws(Ctx x) {
 				if (n + 2 < nChunks) fill(n + 2); // in flight while chunk n+1 is produced: touches ring slots / buffers nobody reads now
 				if (n >= 1) writeback(n - 1);
 				__syncwarp();
-				if (n + 1 < nChunks) produce(n + 1);
+				if (n + 1 < nChunks) produce_any(n + 1);
 			}
 			__syncthreads();
 			writeback(nChunks - 1);

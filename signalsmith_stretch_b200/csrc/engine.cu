@@ -49,7 +49,7 @@ struct b200s_engine {
 	int exactMath = 0;         // b200s_set_tuning key 3: 1 = the phase chain in the reference's unfused IEEE arithmetic
 	int nHostParts = 12; // (measured, batch 1024 stereo: 2 -> 15.1, 4 -> 13.0, 8 -> 12.2, 12 -> 11.2, 16 -> 11.8 ms per step) host-buffer API: stream groups whose H2D copy / kernels / D2H copy are pipelined
 	cudaEvent_t evStart = 0, evStop = 0;
-	long long launches = 0;
+	long long launches = 0, allocs = 0;
 	std::string err;
 	// optional per-kernel CUDA-event timing (b200s_profile_begin/end)
 	bool profiling = false;
@@ -112,6 +112,7 @@ template <typename T>
 static int dalloc(b200s_engine *e, T **p, size_t n) {
 	if (*p) cudaFree(*p);
 	*p = 0;
+	++e->allocs;
 	CK(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
 	return 0;
 }
@@ -1042,6 +1043,7 @@ int b200s_timer_stop(b200s_engine *e, float *ms) {
 	return 0;
 }
 long long b200s_kernel_launches(const b200s_engine *e) { return e ? e->launches : 0; }
+long long b200s_device_allocations(const b200s_engine *e) { return e ? e->allocs : 0; }
 int b200s_profile_begin(b200s_engine *e) {
 	if (!e) return B200S_EINVAL;
 	e->profiling = true;

@@ -56,6 +56,13 @@ def run_batch(obj, x, ratio_out, chunk_out):
     return np.concatenate(outs, axis=-1)
 
 
+# piecewise-linear frequency maps (setFreqMap with a tabulated function; frequencies as multiples of the sample rate)
+PWL_MONOTONE = (np.array([0.0, 0.02, 0.08, 0.2, 0.5], np.float32), np.array([0.0, 0.03, 0.1, 0.21, 0.5], np.float32))
+# not monotone: the band between 0.06 and 0.1 folds back below what the band under it maps to, so consecutive peaks can
+# have DEcreasing output bins (updateOutputMap's segments then overwrite each other in peak order, :896-911)
+PWL_FOLDING = (np.array([0.0, 0.06, 0.1, 0.25, 0.5], np.float32), np.array([0.0, 0.09, 0.07, 0.3, 0.5], np.float32))
+
+
 # named configurations (BASELINE.json configs, scaled down where noted)
 def cfg_identity(o):
     o.presetDefault(1, 48000.0)

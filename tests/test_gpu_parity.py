@@ -141,10 +141,12 @@ def test_automatic_formant_pitch_vs_oracle(gpu, oracle_port):
 def test_teacher_forced_block_by_block(gpu, oracle_port, name):
     """T1 of SURVEY.md section 8(c): before every call the oracle's complete signal state (history,
     pending overlap-add, spectra, prediction energy) is imported into the GPU engine, both then
-    process the same 2 blocks; errors cannot accumulate across calls.  Gate: median call <= 1e-5 RMS;
-    every call <= 2e-4 (a pure sine sweep leaves most bins at rounding-noise level, where a hard
-    decision can flip inside a single block: the reference's own two builds disagree by 2.2e-4 on
-    that fixture, tests/golden/make_golden.py)."""
+    process the same 2 blocks; errors cannot accumulate across calls.  Gate: EVERY call <= 1e-5 RMS on the
+    harmonic fixtures (2e-5 with formants: the envelope's running max / min decisions sit on the FFT rounding).
+    The one exception is the pure sine sweep (config 1): most of its bins are at rounding-noise level, where a hard
+    decision can flip inside a single block -- the reference's own two builds (header vs shipped binary) disagree by
+    more than 1e-4 over 2-block windows of that very fixture, which is asserted below from the golden file; there the
+    gate is median <= 1e-5, every call <= 2e-4."""
     cfg, C, sr, ratio, kind = signals.CONFIGS[name]
     e, o = gpu(1), oracle_port()
     cfg(e)
@@ -162,7 +164,15 @@ def test_teacher_forced_block_by_block(gpu, oracle_port, name):
         yo = o.process(xin[0], co)
         yg = np.asarray(e.process(xin, co))[0]
         errs.append(rms(yg - yo))
-    assert np.median(errs) <= 1e-5 and max(errs) <= 2e-4, errs
+    if kind == "sweep":
+        g = np.load(os.path.join(GOLD, name + ".npz"))
+        lat = e.outputLatency() + int(e.inputLatency() * ratio)
+        dd = g["hdr"] - g["wasm"]
+        ref_vs_ref = max(rms(dd[:, lat + k * co: lat + (k + 1) * co]) for k in range((dd.shape[-1] - lat) // co))
+        assert ref_vs_ref > 1e-4, ref_vs_ref  # the reference disagrees with itself by more than the north-star tolerance here
+        assert np.median(errs) <= 1e-5 and max(errs) <= 2e-4, errs
+    else:
+        assert max(errs) <= (2e-5 if name == "config4_formant" else 1e-5), errs
 
 
 def test_identity_full_size_is_a_pure_delay(gpu):
@@ -277,7 +287,7 @@ def test_chain_kernel_generations_agree_bit_exactly(gpu, blocks_per_call):
     exercises the second group / the warp hand-off."""
     cfg, C, sr, ratio, kind = signals.CONFIGS["config2_stereo_0p8x"]
     outs = []
-    for gen in (1, 2, 3, 4):
+    for gen in (1, 2, 3, 4, 5):
         e = gpu(5)
         cfg(e)
         e.set_tuning(0, gen)
@@ -289,6 +299,7 @@ def test_chain_kernel_generations_agree_bit_exactly(gpu, blocks_per_call):
     assert np.array_equal(outs[0], outs[1]), "gen 2 differs: max %g" % np.abs(outs[0] - outs[1]).max()
     assert np.array_equal(outs[0], outs[2]), "gen 3 differs: max %g" % np.abs(outs[0] - outs[2]).max()
     assert np.array_equal(outs[0], outs[3]), "gen 4 differs: max %g" % np.abs(outs[0] - outs[3]).max()
+    assert np.array_equal(outs[0], outs[4]), "gen 5 (warp-specialised) differs: max %g" % np.abs(outs[0] - outs[4]).max()
 
 
 @pytest.mark.gpu
@@ -383,3 +394,101 @@ def test_pcm16_boundary_equals_float_path_with_the_tools_conversions(gpu):
         outs.append(np.concatenate(ys, axis=2))
     assert np.abs(outs[0]).max() > 300
     assert np.array_equal(outs[0], outs[1])
+
+
+# ------------------------------------------------------------------------------------------------
+# parity at the benchmark's shape (BASELINE configs at batch scale, 32 blocks per call, default arithmetic)
+# ------------------------------------------------------------------------------------------------
+def _pool_input(S, C, n, sr, sampled):
+    """[S][C][n]: 32 distinct harmonic streams at the `sampled` indices (seed = index), every other stream a copy of
+    one of them (generating 1024 x 172 800 x 11 sines per test would cost more than the test itself)."""
+    pool = {s: np.stack([signals.harmonic(n, sr, s, c) for c in range(C)]) for s in sampled}
+    keys = list(sampled)
+    return np.stack([pool[s] if s in pool else pool[keys[s % len(keys)]] for s in range(S)])
+
+
+BENCH_SHAPES = [
+    # (name, batch, calls): three 32-block calls, i.e. every lane of the frame wavefront busy, state carried twice
+    ("config2_stereo_0p8x", 1024, 3),
+    ("config3_7st_ton8k", 256, 3),
+    ("config4_formant", 256, 3),
+]
+
+
+@pytest.mark.parametrize("name,S,calls", BENCH_SHAPES, ids=[b[0] for b in BENCH_SHAPES])
+def test_benchmark_shape_vs_oracle(gpu, oracle_port, name, S, calls):
+    """BASELINE configs[1] at its real batch (1024 stereo streams, 0.8x, 32 blocks per call) and configs[2] / [3] at
+    batch 256, default (fast) arithmetic: 32 sampled streams against the oracle.  <= 1e-4 RMS over the first 8 blocks
+    after the latency, <= 1e-3 over the whole 2.9 s (the reference's own criterion, cmd/main-dev.cpp:215-232)."""
+    cfg, C, sr, ratio, kind = signals.CONFIGS[name]
+    e = gpu(S)
+    cfg(e)
+    H = e.intervalSamples()
+    n_out = 32 * H
+    n_in = int(round(n_out / ratio))
+    sampled = [(S // 32) * i + (i % (S // 32)) for i in range(32)]
+    x = _pool_input(S, C, n_in * calls, sr, sampled)
+    y = signals.run_batch(e, x, ratio, n_out)
+    assert y.shape == (S, C, n_out * calls)
+    ref = _oracle_batch(oracle_port, cfg, x[sampled], ratio, n_out)
+    lat = e.outputLatency() + int(e.inputLatency() * ratio)
+    d = y[sampled] - ref
+    head = np.array([rms(d[i][:, : lat + 8 * H]) for i in range(len(sampled))])
+    whole = np.array([rms(d[i]) for i in range(len(sampled))])
+    assert head.max() <= 1e-4, (head.max(), np.median(head))
+    assert whole.max() <= 1e-3, (whole.max(), np.median(whole))
+    # copies of the same input in different batch lanes agree bit for bit
+    twin = next(s for s in range(S) if s not in sampled and s % len(sampled) == 0)
+    assert np.array_equal(y[twin], y[sampled[0]])
+
+
+@pytest.mark.parametrize("which", ["monotone", "folding"])
+def test_set_freq_map_table_vs_oracle(gpu, oracle_port, which):
+    """setFreqMap through the C ABI on the GPU (row f3): a monotone piecewise-linear map and one that folds back
+    (non-monotone output map, :896-911), presetDefault stereo, several calls."""
+    tab = signals.PWL_MONOTONE if which == "monotone" else signals.PWL_FOLDING
+
+    def cfg(o):
+        o.presetDefault(2, 48000.0)
+        o.setFreqMapTable(*tab)
+
+    S = 4
+    e = gpu(S)
+    cfg(e)
+    H, B = e.intervalSamples(), e.blockSamples()
+    n_out = 12 * H + B
+    x = signals.batch("harmonic", S, 2, n_out, 48000)
+    y = signals.run_batch(e, x, 1.0, 6 * H)
+    ref = _oracle_batch(oracle_port, cfg, x, 1.0, 6 * H)
+    lat = e.outputLatency() + e.inputLatency()
+    d = y - ref
+    per = np.array([rms(d[s][:, : lat + 8 * H]) for s in range(S)])
+    assert np.median(per) <= 1e-4, per
+    assert per.max() <= 1e-3 and rms(d) <= 1e-3, (per, rms(d))
+
+
+@pytest.mark.parametrize("name", ["config2_stereo_0p8x", "config4_formant"])
+def test_no_device_allocation_in_process_after_reserve(gpu, name):
+    """The reference's real-time contract (cmd/main-dev.cpp:158-163: no allocation inside process()): after
+    b200s_reserve() with the call sizes -- parameters set first -- process() performs no cudaMalloc."""
+    import torch
+
+    cfg, C, sr, ratio, kind = signals.CONFIGS[name]
+    S = 16
+    e = gpu(S)
+    cfg(e)
+    H = e.intervalSamples()
+    n_out = 8 * H
+    n_in = int(round(n_out / ratio))
+    e.reserve(n_in, n_out)
+    x = signals.batch(kind, S, C, 3 * n_in, sr)
+    before = e.device_allocations()
+    for k in range(3):  # host-buffer API
+        e.process(x[:, :, k * n_in:(k + 1) * n_in], n_out)
+    xd = torch.from_numpy(np.ascontiguousarray(x[:, :, :n_in])).cuda()
+    torch.cuda.synchronize()
+    e.process(xd, n_out)  # device-pointer API
+    e.process(x[:, :, : n_in // 2], n_out // 2)  # smaller calls fit too
+    e.synchronize()
+    assert e.device_allocations() == before
+    assert before > 0

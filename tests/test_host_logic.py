@@ -169,6 +169,53 @@ def test_baseline_configurations_full_size_bit_exact_vs_oracle(emu_libs, oracle_
     assert np.array_equal(y, ref), "max diff %g" % np.abs(y - ref).max()
 
 
+FREQ_MAPS = [
+    ("pwl_monotone_K256", lambda o: (o.configure(2, 512, 128), o.setFreqMapTable(*signals.PWL_MONOTONE)), 2, 1.0, 4000, 640),
+    ("pwl_folding_K256_0.8x", lambda o: (o.configure(1, 512, 128), o.setFreqMapTable(*signals.PWL_FOLDING)), 1, 0.8, 4000, 640),
+    ("pwl_folding_default_stereo", lambda o: (o.presetDefault(2, 48000.0), o.setFreqMapTable(*signals.PWL_FOLDING)), 2, 1.0, 20000, 5760),
+    ("pwl_monotone_formant_comp", lambda o: (o.configure(2, 512, 128), o.setFreqMapTable(*signals.PWL_MONOTONE), o.setFormantFactor(1, True), o.setFormantBase(200 / 48000)), 2, 1.0, 4000, 640),
+]
+
+
+@pytest.mark.parametrize("name,cfg,C,ratio,n,chunk", FREQ_MAPS, ids=[c[0] for c in FREQ_MAPS])
+def test_set_freq_map_table_bit_exact_vs_oracle(emu_libs, oracle_port, name, cfg, C, ratio, n, chunk):
+    """setFreqMap (:120-122) through b200s_set_freq_map_table: the per-peak mapFreq (:874), the formant target map
+    (:1020) and -- with a map that folds back -- the non-monotone output-map replay, on the CUDA kernels."""
+    x = signals.batch("harmonic", 2, C, n, 48000)
+    g = _emu(emu_libs["exact"], 2)
+    cfg(g)
+    y = signals.run_batch(g, x, ratio, chunk)
+    ref = _oracle_batch(oracle_port, cfg, x, ratio, chunk)
+    assert np.array_equal(y, ref), "max diff %g" % np.abs(y - ref).max()
+
+
+def test_tabulated_smooth_map_error_is_small(emu_libs, oracle_port):
+    """The facade tabulates a callable on 2049 points (include/signalsmith-stretch/signalsmith-stretch.h): for a smooth
+    map (the oracle's quadratic stand-in) the piecewise-linear table deviates by < 1e-7 of the sample rate, and the
+    output stays within the short-horizon tolerance of the analytic map."""
+    a, b = 1.2, 0.5
+    fin = np.linspace(0.0, 0.5, 2049).astype(np.float32)
+    fout = (np.float32(a) * fin + np.float32(b) * fin * fin).astype(np.float32)
+    mid = ((fin[1:].astype(np.float64) + fin[:-1]) / 2)
+    assert np.abs((fout[1:].astype(np.float64) + fout[:-1]) / 2 - (a * mid + b * mid * mid)).max() < 1e-7
+    x = signals.batch("harmonic", 1, 2, 6000, 48000)
+
+    def cfg_tab(o):
+        o.configure(2, 512, 128)
+        o.setFreqMapTable(fin, fout)
+
+    def cfg_quad(o):
+        o.configure(2, 512, 128)
+        o.setFreqMapQuadratic(a, b)
+
+    g = _emu(emu_libs["exact"], 1)
+    cfg_tab(g)
+    y = signals.run_batch(g, x, 1.0, 640)
+    ref = _oracle_batch(oracle_port, cfg_quad, x, 1.0, 640)
+    lat = g.outputLatency() + g.inputLatency()
+    assert rms((y - ref)[..., : lat + 8 * 128]) <= 1e-4
+
+
 def test_parameters_change_between_calls_bit_exact_vs_oracle(emu_libs, oracle_port):
     """Switching between the kernel paths from call to call -- plain stereo (packed direct chain on interleaved spectra,
     state carried through k_plan / k_commit in both layouts), frequency map (k_prep + generic chain), formants with

@@ -117,6 +117,9 @@ def test_live_oracle_bit_exact_vs_reference_header(oracle_port):
         (lambda o: (o.presetCheaper(2, 48000.0, False), o.setTransposeSemitones(4, 0.2), o.setFormantSemitones(3, False), o.setFormantBase(0)), 1.0, 480),
         (lambda o: (o.configure(2, 1000, 250, True), o.setFreqMapQuadratic(1.2, 0.5)), 0.9, 333),
         (lambda o: o.presetDefault(2, 44100.0), 2.5, 441),  # > 2x: exercises the RNG path of the header
+        # setFreqMap with a piecewise-linear function: monotone, and one that folds back (non-monotone output map)
+        (lambda o: (o.configure(2, 1000, 250, False), o.setFreqMapTable(*signals.PWL_MONOTONE)), 1.0, 500),
+        (lambda o: (o.presetDefault(2, 48000.0), o.setFreqMapTable(*signals.PWL_FOLDING)), 1.25, 2880),
     ]
     for cfg, ratio, chunk in cases:
         h, o = CpuStretch("hdr"), oracle_port()
