@@ -8,6 +8,7 @@
 //   stPredE  [S][C][K]          Prediction::energy of the last block (:593)
 // and per process() call scratch, F = blocks in the call:
 //   spec     [S][2F][C][K] float2   analysis spectra (slot 2f: block f, slot 2f+1: its re-analysed predecessor)
+//   cS, cM   [S][F][K]              smoothed energy / formant envelope of the block (mapped / formant calls only)
 //   cE       [S][F][C][K]           Prediction::energy
 //   cPI,cFT,cT1,cT2 [S][F][C][K] float2   Prediction::input, freqTwist, short/long vertical twists
 //   Y        [S][F][C][K] float2    final Band::output of every block
@@ -126,6 +127,7 @@ struct Ctx {
 	int inAligned; // input / history rows allow 16-byte cp.async (pointer, strides and lengths multiples of 4 floats)
 	float2 *spec, *Y, *cPI, *cFT, *cT1, *cT2;
 	float *cE;
+	float *cS, *cM; // [S][maxFrames][K]: smoothed energy (:816-848) and formant envelope (:986-1007) of every block: k_energy / k_passes -> k_prep
 	float *cPitch; // [S][maxFrames] freqEstimate of every block when formantBaseFreq <= 0 (k_pitch)
 	// sub-batch of streams this launch covers (the batch is processed as a few sub-batches on
 	// prioritised CUDA streams so that different kernels of the sequence overlap on the SMs)

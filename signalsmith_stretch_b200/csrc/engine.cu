@@ -77,7 +77,7 @@ struct b200s_engine {
 	Job *dJobs = 0;
 	int numSMs = 148;
 	float2 *dSpec = 0, *dY = 0, *dPI = 0, *dFT = 0, *dT1 = 0, *dT2 = 0;
-	float *dE = 0;
+	float *dE = 0, *dS = 0, *dM = 0;
 	float *dStPitch = 0, *dPitch = 0;
 	// staging for the host-buffer API and for flush/outputSeek
 	float *dIn = 0, *dOut = 0, *dZero = 0, *dTmp = 0;
@@ -126,7 +126,7 @@ static void free_all(b200s_engine *e) {
 	dfree(e->dWindow); dfree(e->dWinProd); dfree(e->dWpReset); dfree(e->dRot); dfree(e->dTwiddle); dfree(e->dPretw); dfree(e->dAnaTab);
 	dfree(e->dSched); dfree(e->dHist[0]); dfree(e->dHist[1]); dfree(e->dPend); dfree(e->dPendWp);
 	dfree(e->dStIn); dfree(e->dStPrev); dfree(e->dStOut); dfree(e->dStPredE); dfree(e->dStIl);
-	dfree(e->dFrames); dfree(e->dCall); dfree(e->dJobs); dfree(e->dSpec); dfree(e->dY); dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dE); dfree(e->dStPitch); dfree(e->dPitch);
+	dfree(e->dFrames); dfree(e->dCall); dfree(e->dJobs); dfree(e->dSpec); dfree(e->dY); dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dE); dfree(e->dS); dfree(e->dM); dfree(e->dStPitch); dfree(e->dPitch);
 	dfree(e->dIn); dfree(e->dOut); dfree(e->dZero); dfree(e->dTmp); dfree(e->dIn16); dfree(e->dOut16);
 	e->in16Cap = e->out16Cap = 0;
 	e->maxFrames = e->coefFrames = 0;
@@ -151,7 +151,7 @@ static Ctx make_ctx(b200s_engine *e) {
 	x.maxFrames = e->maxFrames;
 	x.sBase = 0; x.sCount = e->S;
 	x.frames = e->dFrames; x.call = e->dCall; x.jobs = e->dJobs;
-	x.spec = e->dSpec; x.Y = e->dY; x.cPI = e->dPI; x.cFT = e->dFT; x.cT1 = e->dT1; x.cT2 = e->dT2; x.cE = e->dE; x.stPitch = e->dStPitch; x.cPitch = e->dPitch;
+	x.spec = e->dSpec; x.Y = e->dY; x.cPI = e->dPI; x.cFT = e->dFT; x.cT1 = e->dT1; x.cT2 = e->dT2; x.cE = e->dE; x.cS = e->dS; x.cM = e->dM; x.stPitch = e->dStPitch; x.cPitch = e->dPitch;
 	return x;
 }
 
@@ -250,7 +250,9 @@ static int chain_version(const Cfg &g, int override, int forceFftV1) {
 		const char *v = getenv("B200S_CHAIN_V");
 		env = v ? atoi(v) : 0;
 	}
-	int want = override ? override : env ? env : 5;
+	// default 4: measured on B200 (profiles/r02_chain_ws_ncu_summary.md) the warp-specialised kernel (5) is slower,
+	// 1.95 vs 1.68 ms -- its tile hand-off doubles the shared-memory traffic per step and the consumer waits for the producer
+	int want = override ? override : env ? env : 4;
 	if (want >= 3 && !(g.C == 2 && use_pair_fft(g, forceFftV1))) want = 2;
 	if (want == 5 && g.L > 4) want = 4; // k_chain_ws is laid out for L <= 4 (both presets)
 	return want;
@@ -508,7 +510,7 @@ static int ensure_scratch(b200s_engine *e, int nOut) {
 	if ((rc = dalloc(e, &e->dPitch, (size_t)g.S * need))) return rc;
 	e->maxFrames = need;
 	// the complex coefficient rows follow maxFrames (their row offsets use it) but only exist once a call needed them
-	dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2);
+	dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dS); dfree(e->dM);
 	e->coefFrames = 0;
 	return 0;
 }
@@ -528,6 +530,8 @@ static int ensure_coef(b200s_engine *e) {
 	if ((rc = dalloc(e, &e->dFT, n))) return rc;
 	if ((rc = dalloc(e, &e->dT1, n))) return rc;
 	if ((rc = dalloc(e, &e->dT2, n))) return rc;
+	if ((rc = dalloc(e, &e->dS, n / g.C))) return rc; // smoothed energy / formant envelope rows: one per block (k_passes)
+	if ((rc = dalloc(e, &e->dM, n / g.C))) return rc;
 	e->coefFrames = e->maxFrames;
 	return 0;
 }
@@ -620,7 +624,18 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 					B200S_LAUNCH(k_pitch, dim3(x.sCount), dim3(kThreads), sizeof(float) * g.K, st, x);
 					CKL();
 				}
-				if (!plain) PROF(PK_PREP, B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g, formantsOn), st, x));
+				if (!plain) {
+					int _rc;
+					if ((_rc = prof_mark(e, PK_PREP, true))) return _rc;
+					// the serial one-pole passes over the bins, one lane per block (kernels.cuh), then the per-bin products
+					B200S_LAUNCH(k_energy, dim3(F, x.sCount), dim3(kThreads), 0, st, x);
+					CKL();
+					B200S_LAUNCH(k_passes, dim3(x.sCount), dim3(32), 0, st, x);
+					CKL();
+					B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g, formantsOn), st, x);
+					CKL();
+					if ((_rc = prof_mark(e, PK_PREP, false))) return _rc;
+				}
 				if (plain && chainV == 5) {
 					int _rc;
 					if ((_rc = prof_mark(e, PK_CHAIN, true))) return _rc;

@@ -435,8 +435,27 @@ def test_benchmark_shape_vs_oracle(gpu, oracle_port, name, S, calls):
     d = y[sampled] - ref
     head = np.array([rms(d[i][:, : lat + 8 * H]) for i in range(len(sampled))])
     whole = np.array([rms(d[i]) for i in range(len(sampled))])
+    mid = np.array([rms(d[i][:, : lat + 16 * H]) for i in range(len(sampled))])
     assert head.max() <= 1e-4, (head.max(), np.median(head))
-    assert whole.max() <= 1e-3, (whole.max(), np.median(whole))
+    # 16 blocks: the horizon of the reference's own regression fixtures and criterion (-60 dB, cmd/main-dev.cpp:215-232)
+    assert mid.max() <= 1e-3, (mid.max(), np.median(mid))
+    # the whole 2.9 s (96 blocks): the recurrence is chaotic (the reference's
+    # output moves by 3e-4 ... 8e-3 RMS within 1-10 s under a 1e-7 input perturbation), so SURVEY.md 8(c) T3 gates the
+    # long horizon on level match and bounds the raw difference by that self-divergence.  Measured on B200: median
+    # 2.8e-3, max 4.8e-3 for configs[1]; the oracle against the reference's own shipped binary (a different build of
+    # the same code) is asserted below to be just as far apart on one of these streams.
+    assert whole.max() <= 1e-2, (whole.max(), np.median(whole))
+    lvl = np.array([20 * np.log10(rms(y[s]) / rms(ref[i])) for i, s in enumerate(sampled)])
+    assert np.abs(lvl).max() <= 0.1, lvl
+    from oracle import wasmref
+
+    if wasmref.available() and name == "config2_stereo_0p8x":
+        w = wasmref.WasmStretch()
+        cfg(w)
+        rw = signals.run_single(w, x[sampled[0]], ratio, n_out)
+        ref_vs_ref = rms(rw - ref[0])
+        print("reference (shipped binary) vs oracle over %d blocks: %.2e RMS; GPU vs oracle: %.2e" % (32 * calls, ref_vs_ref, whole[0]))
+        assert ref_vs_ref >= 1e-3, ref_vs_ref  # (3.96e-3 measured: the reference does not meet 1e-3 against itself at this horizon)
     # copies of the same input in different batch lanes agree bit for bit
     twin = next(s for s in range(S) if s not in sampled and s % len(sampled) == 0)
     assert np.array_equal(y[twin], y[sampled[0]])
