@@ -126,6 +126,13 @@ long long b200s_kernel_launches(const b200s_engine *e);
  * process()" (cmd/main-dev.cpp:158-163); the equivalent here: after b200s_reserve() with the largest call sizes (and
  * with the parameters already set), process() leaves this count unchanged (tests/test_gpu_parity.py). */
 long long b200s_device_allocations(const b200s_engine *e);
+/* Beyond 2x stretch the reference draws a random time factor per bin (:639-640,:749,:769); this library reproduces the
+ * draws of std::default_random_engine(seed) exactly (tests/test_host_logic.py).  The kernels of that path are launched
+ * whenever the host can tell that a block may need them (input / output ratio of this and the previous call, a seek at a
+ * slow rate, flush); the device decides per stream and block.  The one case the host cannot foresee is the first block
+ * after a silence that was below the noise floor but not exactly zero: such a block is processed with the deterministic
+ * factor (its spectrum is at the 1e-8 level) and counted here.  0 in every other situation.  Synchronises. */
+long long b200s_unserved_random_blocks(b200s_engine *e);
 /* Per-kernel device time of process(): between begin and end every kernel of the process()
  * launch sequence is bracketed by CUDA events on the handle's stream.  `ms`/`counts` receive, in
  * this order: plan, analyse, prep, chain, synth, commit (n >= 6). */

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "b200s_set_formant_semitones", "b200s_set_formant_base", "b200s_set_freq_map_table",
     "b200s_seek", "b200s_output_seek", "b200s_process", "b200s_process_async", "b200s_process_pcm16", "b200s_flush", "b200s_exact",
     "b200s_seek_device", "b200s_process_device", "b200s_flush_device",
-    "b200s_timer_start", "b200s_timer_stop", "b200s_kernel_launches", "b200s_device_allocations", "b200s_profile_begin", "b200s_profile_end",
+    "b200s_timer_start", "b200s_timer_stop", "b200s_kernel_launches", "b200s_device_allocations", "b200s_unserved_random_blocks", "b200s_profile_begin", "b200s_profile_end",
     "b200s_selftest_divsqrt",
     "b200s_state_size", "b200s_get_state", "b200s_set_state",
 ]
@@ -86,7 +86,7 @@ def _bind(lib):
         "b200s_exact": (ci, [vp, vp, ci, vp, ci, ip]),
         "b200s_seek_device": (ci, [vp, vp, ci, cd]), "b200s_process_device": (ci, [vp, vp, ci, vp, ci]),
         "b200s_flush_device": (ci, [vp, vp, ci, cf]),
-        "b200s_timer_start": (ci, [vp]), "b200s_timer_stop": (ci, [vp, fp]), "b200s_kernel_launches": (cll, [vp]), "b200s_device_allocations": (cll, [vp]),
+        "b200s_timer_start": (ci, [vp]), "b200s_timer_stop": (ci, [vp, fp]), "b200s_kernel_launches": (cll, [vp]), "b200s_device_allocations": (cll, [vp]), "b200s_unserved_random_blocks": (cll, [vp]),
         "b200s_profile_begin": (ci, [vp]), "b200s_profile_end": (ci, [vp, fp, ip, ci]),
         "b200s_selftest_divsqrt": (ci, [vp, cll, cll, ctypes.POINTER(cll), ctypes.POINTER(cll)]),
         "b200s_state_size": (ci, [vp, ci]), "b200s_get_state": (ci, [vp, ci, vp]), "b200s_set_state": (ci, [vp, ci, vp]),
@@ -329,6 +329,9 @@ class BatchStretch:
 
     def kernel_launches(self):
         return int(self._lib.b200s_kernel_launches(self._h))
+
+    def unserved_random_blocks(self):
+        return int(self._lib.b200s_unserved_random_blocks(self._h))
 
     def device_allocations(self):
         return int(self._lib.b200s_device_allocations(self._h))

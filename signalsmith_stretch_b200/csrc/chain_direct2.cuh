@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(32 * CH2_MAXW) k_chain_direct2(Ctx x) {
 	const int s = x.sBase + blockIdx.x;
 	const Call cl = x.call[s];
 	if (cl.nFrames == 0) return;
+	if (cl.hasRandom && x.randomPathOn) return; // a block beyond 2x stretch draws random time factors: k_prep + k_chain take the stream
 	Chain2Sync &SY = *(Chain2Sync *)dyn_smem;
 	Chain2Tiles<CT> &U = ((Chain2Tiles<CT> *)((char *)dyn_smem + 64))[warp];
 	Chain2Tiles<CT> &UN = ((Chain2Tiles<CT> *)((char *)dyn_smem + 64))[warp + 1 < nWarps ? warp + 1 : warp]; // successor's tiles

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(32) k_chain_direct3(Ctx x) {
 	const int s = x.sBase + blockIdx.x;
 	const Call cl = x.call[s];
 	if (cl.nFrames == 0) return;
+	if (cl.hasRandom && x.randomPathOn) return; // a block beyond 2x stretch draws random time factors: k_prep + k_chain take the stream
 	constexpr int D = LT + 1;
 	Chain3Tiles &U = *(Chain3Tiles *)dyn_smem;
 	// chunk fill: lane -> (bin offset, row within a group of 4); a quarter-warp covers 4 bins (64 B) of 2 rows

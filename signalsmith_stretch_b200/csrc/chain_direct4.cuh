@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(32) k_chain_direct4(Ctx x) {
 	const int s = x.sBase + blockIdx.x;
 	const Call cl = x.call[s];
 	if (cl.nFrames == 0) return;
+	if (cl.hasRandom && x.randomPathOn) return; // a block beyond 2x stretch draws random time factors: k_prep + k_chain take the stream
 	if (x.wsRan && ws_stream_ok(x, s, cl.nFrames, lane)) return; // k_chain_ws has done this stream
 	constexpr int G = LT + 2; // lane skew in bins
 	constexpr int NF = LT + 1; // FIFO entries: bins b .. b+L of the lane's block

@@ -72,6 +72,7 @@ struct Sched {
 	int didSeek;
 	int silenceFirst;
 	float seekTimeFactor;
+	long long zeroRun; // input samples, counted back from the newest, known to be exactly 0.0f (>= histLen: the history is all zeros)
 };
 
 // one block of the schedule (:281-319)
@@ -81,6 +82,7 @@ struct Frame {
 	int flags;
 	float timeFactor; // :312, before the clamp of :638
 	int inSlot, prevSlot; // spectrum slots: 0 = stIn, 1 = stPrev, 2+2f / 3+2f = this call's analyses
+	unsigned rng;         // FR_RANDOM: state of the stream's random engine before this block's 2K-2 draws (:749,:769)
 };
 
 // per-stream result of the planner for one process() call
@@ -89,6 +91,7 @@ struct Call {
 	int nFrames;
 	int finalIn, finalPrev; // slots that become stIn / stPrev after the call
 	int nJobs;              // analyses of this call (entries of the stream's Job list)
+	int hasRandom;          // some block of the call stretches beyond 2x (:639): the stream takes the k_prep + k_chain path
 };
 
 // one windowed analysis FFT of the call (:333-376): block samples start at stream index `start`
@@ -127,6 +130,16 @@ struct Ctx {
 	int inAligned; // input / history rows allow 16-byte cp.async (pointer, strides and lengths multiples of 4 floats)
 	float2 *spec, *Y, *cPI, *cFT, *cT1, *cT2;
 	float *cE;
+	// random time factors beyond 2x stretch (:639-640,:749,:769).  The reference draws from std::default_random_engine
+	// (libstdc++: minstd_rand0, x <- 16807 x mod 2^31-1) through uniform_real_distribution<float>, 2K-2 draws per block in
+	// bin order; draw i of a block is state * 16807^i, so every bin finds its draws by one modular multiplication.
+	unsigned *rngState;     // [S] engine state per stream (persists over reset / configure, like the reference's member)
+	const unsigned *rngPow; // [2K] 16807^i mod 2^31-1
+	unsigned rngJump;       // 16807^(2K-2): one block's worth of draws
+	int randomPathOn;       // the kernels of the random path run in this call: the direct chain kernels leave hasRandom streams to them
+	unsigned long long *diag; // [1] blocks whose random time factors could not be honoured (random path not launched; see engine.cu)
+	int randomOnly;         // k_prep / k_chain launched beside the direct chain kernels: only streams with Call::hasRandom
+	float2 *cT1u, *cT2u;    // [S][F][C][K] the "upwards" twists of a random block (:769-781; the downwards ones are cT1 / cT2)
 	float *cS, *cM; // [S][maxFrames][K]: smoothed energy (:816-848) and formant envelope (:986-1007) of every block: k_energy / k_passes -> k_prep
 	float *cPitch; // [S][maxFrames] freqEstimate of every block when formantBaseFreq <= 0 (k_pitch)
 	// sub-batch of streams this launch covers (the batch is processed as a few sub-batches on

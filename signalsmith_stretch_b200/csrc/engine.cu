@@ -78,6 +78,14 @@ struct b200s_engine {
 	int numSMs = 148;
 	float2 *dSpec = 0, *dY = 0, *dPI = 0, *dFT = 0, *dT1 = 0, *dT2 = 0;
 	float *dE = 0, *dS = 0, *dM = 0;
+	// random time factors beyond 2x stretch (:639-640): engine state per stream (lives as long as the handle, like the
+	// reference's randomEngine member), powers of the multiplier, the upwards twists of random blocks
+	unsigned *dRng = 0, *dRngPow = 0;
+	unsigned long long *dDiag = 0;
+	unsigned rngJump = 1;
+	float2 *dT1u = 0, *dT2u = 0;
+	int randFrames = 0;
+	bool prevCallMayRandom = false, seekMayRandom = false;
 	float *dStPitch = 0, *dPitch = 0;
 	// staging for the host-buffer API and for flush/outputSeek
 	float *dIn = 0, *dOut = 0, *dZero = 0, *dTmp = 0;
@@ -126,7 +134,8 @@ static void free_all(b200s_engine *e) {
 	dfree(e->dWindow); dfree(e->dWinProd); dfree(e->dWpReset); dfree(e->dRot); dfree(e->dTwiddle); dfree(e->dPretw); dfree(e->dAnaTab);
 	dfree(e->dSched); dfree(e->dHist[0]); dfree(e->dHist[1]); dfree(e->dPend); dfree(e->dPendWp);
 	dfree(e->dStIn); dfree(e->dStPrev); dfree(e->dStOut); dfree(e->dStPredE); dfree(e->dStIl);
-	dfree(e->dFrames); dfree(e->dCall); dfree(e->dJobs); dfree(e->dSpec); dfree(e->dY); dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dE); dfree(e->dS); dfree(e->dM); dfree(e->dStPitch); dfree(e->dPitch);
+	dfree(e->dFrames); dfree(e->dCall); dfree(e->dJobs); dfree(e->dSpec); dfree(e->dY); dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dE); dfree(e->dS); dfree(e->dM); dfree(e->dT1u); dfree(e->dT2u); dfree(e->dRngPow); dfree(e->dStPitch);
+	e->randFrames = 0; dfree(e->dPitch);
 	dfree(e->dIn); dfree(e->dOut); dfree(e->dZero); dfree(e->dTmp); dfree(e->dIn16); dfree(e->dOut16);
 	e->in16Cap = e->out16Cap = 0;
 	e->maxFrames = e->coefFrames = 0;
@@ -151,7 +160,8 @@ static Ctx make_ctx(b200s_engine *e) {
 	x.maxFrames = e->maxFrames;
 	x.sBase = 0; x.sCount = e->S;
 	x.frames = e->dFrames; x.call = e->dCall; x.jobs = e->dJobs;
-	x.spec = e->dSpec; x.Y = e->dY; x.cPI = e->dPI; x.cFT = e->dFT; x.cT1 = e->dT1; x.cT2 = e->dT2; x.cE = e->dE; x.cS = e->dS; x.cM = e->dM; x.stPitch = e->dStPitch; x.cPitch = e->dPitch;
+	x.spec = e->dSpec; x.Y = e->dY; x.cPI = e->dPI; x.cFT = e->dFT; x.cT1 = e->dT1; x.cT2 = e->dT2; x.cE = e->dE; x.cS = e->dS; x.cM = e->dM; x.cT1u = e->dT1u; x.cT2u = e->dT2u;
+	x.rngState = e->dRng; x.rngPow = e->dRngPow; x.rngJump = e->rngJump; x.diag = e->dDiag; x.stPitch = e->dStPitch; x.cPitch = e->dPitch;
 	return x;
 }
 
@@ -438,6 +448,27 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 		CK(cudaMemcpy(e->dAnaTab, tab.data(), sizeof(float4) * g.K, cudaMemcpyHostToDevice));
 	}
 
+	{ // powers of the random engine's multiplier: draw i of a block is state * 16807^i mod 2^31-1 (kernels.cuh)
+		std::vector<unsigned> pw(2 * (size_t)g.K);
+		unsigned v = 1;
+		for (size_t i = 0; i < pw.size(); ++i) {
+			pw[i] = v;
+			v = rng_mulmod(v, B200S_RNG_A);
+		}
+		e->rngJump = pw[2 * (size_t)g.K - 2];
+		if ((rc = dalloc(e, &e->dRngPow, pw.size()))) return rc;
+		CK(cudaMemcpy(e->dRngPow, pw.data(), sizeof(unsigned) * pw.size(), cudaMemcpyHostToDevice));
+		if (!e->dRng) { // std::default_random_engine(seed): state = seed mod (2^31-1), 1 if that is 0; NOT touched by configure / reset
+			if ((rc = dalloc(e, &e->dRng, (size_t)g.S))) return rc;
+			unsigned x0 = (unsigned)((unsigned long long)e->seed % (unsigned long long)B200S_RNG_M);
+			if (x0 == 0) x0 = 1;
+			std::vector<unsigned> st((size_t)g.S, x0);
+			CK(cudaMemcpy(e->dRng, st.data(), sizeof(unsigned) * st.size(), cudaMemcpyHostToDevice));
+			if ((rc = dalloc(e, &e->dDiag, (size_t)1))) return rc;
+			CK(cudaMemset(e->dDiag, 0, sizeof(unsigned long long)));
+		}
+	}
+
 	// ---- state
 	const size_t SC = (size_t)g.S * g.C;
 	if ((rc = dalloc(e, &e->dSched, g.S))) return rc;
@@ -464,6 +495,7 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 			s.didSeek = 0;
 			s.silenceFirst = 1;
 			s.seekTimeFactor = 1;
+			s.zeroRun = B200S_NEVER;
 		}
 		CK(cudaMemcpy(e->dSched, sc.data(), sizeof(Sched) * g.S, cudaMemcpyHostToDevice));
 	}
@@ -510,8 +542,8 @@ static int ensure_scratch(b200s_engine *e, int nOut) {
 	if ((rc = dalloc(e, &e->dPitch, (size_t)g.S * need))) return rc;
 	e->maxFrames = need;
 	// the complex coefficient rows follow maxFrames (their row offsets use it) but only exist once a call needed them
-	dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dS); dfree(e->dM);
-	e->coefFrames = 0;
+	dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dS); dfree(e->dM); dfree(e->dT1u); dfree(e->dT2u);
+	e->coefFrames = e->randFrames = 0;
 	return 0;
 }
 // Complex coefficient rows of k_prep (32 B per bin-channel and block: 6.6 GB at batch 1024 x 33 blocks stereo): only calls
@@ -533,6 +565,18 @@ static int ensure_coef(b200s_engine *e) {
 	if ((rc = dalloc(e, &e->dS, n / g.C))) return rc; // smoothed energy / formant envelope rows: one per block (k_passes)
 	if ((rc = dalloc(e, &e->dM, n / g.C))) return rc;
 	e->coefFrames = e->maxFrames;
+	return 0;
+}
+// the two extra twist rows of blocks with random time factors (calls that may stretch beyond 2x only)
+static int ensure_rand(b200s_engine *e) {
+	if (e->randFrames == e->maxFrames && e->dT1u) return 0;
+	const Cfg &g = e->cfg;
+	CK(cudaStreamSynchronize(e->stream));
+	const size_t n = (size_t)g.S * e->maxFrames * g.C * g.K;
+	int rc;
+	if ((rc = dalloc(e, &e->dT1u, n))) return rc;
+	if ((rc = dalloc(e, &e->dT2u, n))) return rc;
+	e->randFrames = e->maxFrames;
 	return 0;
 }
 static int ensure_buf(b200s_engine *e, float **p, size_t *cap, size_t n, bool zero) {
@@ -559,8 +603,21 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	}
 	int rc;
 	if ((rc = ensure_scratch(e, nOut))) return rc;
-	if (!params_plain(e) && (rc = ensure_coef(e))) return rc;
+	// Can a block of this call stretch beyond 2x (timeFactor = interval / inputInterval > 2, :312,:639)?  Inside a call the
+	// input interval is interval * nIn / nOut give or take a sample; the first block's mixes in the previous call's ratio;
+	// after a seek it is 1 / playbackRate.  Conservative on purpose: the decision itself is taken per stream on the device
+	// (k_plan sets Call::hasRandom); this only says whether the kernels of the random path have to be launched at all.
+	const bool lowRatio = nOut > 0 && (long long)nIn * 2 * g.H < (long long)nOut * (g.H + 4);
+	const bool mayRandom = nOut > 0 && (lowRatio || e->prevCallMayRandom || e->seekMayRandom);
+	if (nOut > 0) {
+		e->prevCallMayRandom = lowRatio;
+		e->seekMayRandom = false;
+	}
+	if ((!params_plain(e) || mayRandom) && (rc = ensure_coef(e))) return rc;
+	if (mayRandom && (rc = ensure_rand(e))) return rc;
 	Ctx x = make_ctx(e);
+	if (!mayRandom) x.cT1u = x.cT2u = nullptr; // (stale rows of an earlier call are never read)
+	x.randomPathOn = (mayRandom || !params_plain(e)) ? 1 : 0; // mapped / formant calls run k_prep + k_chain for every stream anyway
 	x.in = dIn; x.out = dOut; x.nIn = nIn; x.nOut = nOut;
 	x.inChanStride = inChanStride; x.inStreamStride = inStreamStride;
 	x.outChanStride = outChanStride; x.outStreamStride = outStreamStride;
@@ -660,6 +717,19 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 					PROF(PK_CHAIN, B200S_LAUNCH(kc, grid, block, smem_chain(g, plain), st, x));
 				}
 			}
+			if (F > 0 && plain && mayRandom) {
+				// streams with a block beyond 2x stretch (Call::hasRandom): the direct chain kernels above returned at once for
+				// them; k_prep forms their coefficient rows with the per-bin random time factors and the generic chain runs
+				// them.  Every other CTA of these two launches exits immediately.
+				x.randomOnly = 1;
+				B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g, false), st, x);
+				CKL();
+				dim3 grid((x.sCount + kChainWarps - 1) / kChainWarps), block(32 * kChainWarps);
+				ChainKernel kc = chain_kernel(g, false);
+				B200S_LAUNCH(kc, grid, block, smem_chain(g, false), st, x);
+				CKL();
+				x.randomOnly = 0;
+			}
 			if (pairFft) {
 				PROF(PK_SYNTH, B200S_LAUNCH(synth2_kernel(g), dim3(g.C, x.sCount), dim3(256), smem_synth2(g), st, x));
 			} else {
@@ -692,6 +762,7 @@ static int seek_impl(b200s_engine *e, const float *dIn, int chanStride, long lon
 	Ctx x = make_ctx(e);
 	x.in = dIn; x.nIn = n; x.inChanStride = chanStride; x.inStreamStride = streamStride;
 	float stf = (playbackRate * g.H > 1) ? float(1 / playbackRate) : float(g.H); // :164
+	e->seekMayRandom = stf > 1.9f; // the next block takes this as its time factor (:312)
 	B200S_LAUNCH(k_seek, dim3(g.S), dim3(kThreads), 0, e->stream, x, stf);
 	CKL();
 	return 0;
@@ -815,6 +886,8 @@ void b200s_destroy(b200s_engine *e) {
 	free_all(e);
 	dfree(e->dMapIn);
 	dfree(e->dMapOut);
+	dfree(e->dRng);
+	dfree(e->dDiag);
 	for (int i = 0; i < b200s_engine::kMaxSub; ++i) {
 		if (e->subStream[i]) cudaStreamDestroy(e->subStream[i]);
 		if (e->evSubDone[i]) cudaEventDestroy(e->evSubDone[i]);
@@ -1059,6 +1132,12 @@ int b200s_timer_stop(b200s_engine *e, float *ms) {
 }
 long long b200s_kernel_launches(const b200s_engine *e) { return e ? e->launches : 0; }
 long long b200s_device_allocations(const b200s_engine *e) { return e ? e->allocs : 0; }
+long long b200s_unserved_random_blocks(b200s_engine *e) {
+	if (!e || !e->dDiag) return 0;
+	unsigned long long v = 0;
+	if (cudaStreamSynchronize(e->stream) != cudaSuccess || cudaMemcpy(&v, e->dDiag, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+	return (long long)v;
+}
 int b200s_profile_begin(b200s_engine *e) {
 	if (!e) return B200S_EINVAL;
 	e->profiling = true;

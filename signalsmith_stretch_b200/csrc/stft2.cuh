@@ -16,14 +16,6 @@
 
 namespace b200s {
 
-#ifdef B200S_EMU
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) { memcpy(dst, src, 16); }
-#else
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-	unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-}
-#endif
 
 __host__ __device__ __forceinline__ int stage_len(int B) { return (B + 8 + 3) & ~3; }
 

@@ -216,6 +216,81 @@ def test_tabulated_smooth_map_error_is_small(emu_libs, oracle_port):
     assert rms((y - ref)[..., : lat + 8 * 128]) <= 1e-4
 
 
+RANDOM_STRETCH = [
+    # beyond 2x stretch the reference draws a random time factor per bin and direction (:639-640,:749,:769) from
+    # std::default_random_engine(seed): k_plan advances the stream's engine state per block, k_prep forms the twists
+    # with the per-bin draws (one modular multiplication each), the generic chain consumes them
+    ("mono_K256_3x", lambda o: o.configure(1, 512, 128), 1, 3.0, 2000, 1500, 77),
+    ("stereo_K256_2.5x", lambda o: o.configure(2, 512, 128), 2, 2.5, 2000, 1280, 12345),
+    ("stereo_K256_2.5x_+3st_mapped", lambda o: (o.configure(2, 512, 128), o.setTransposeSemitones(3, 0.25)), 2, 2.5, 2000, 1280, 5),
+    ("default_stereo_2.5x_interleaved_spectra", lambda o: o.presetDefault(2, 48000.0), 2, 2.5, 9216, 11520, 3),
+    ("cheaper_mono_4x", lambda o: o.presetCheaper(1, 48000.0), 1, 4.0, 6000, 7680, 2**31 + 9),
+]
+
+
+@pytest.mark.parametrize("name,cfg,C,ratio,n,chunk,seed", RANDOM_STRETCH, ids=[c[0] for c in RANDOM_STRETCH])
+def test_random_time_factors_beyond_2x_bit_exact_vs_oracle(emu_libs, name, cfg, C, ratio, n, chunk, seed):
+    from oracle.hdrref import CpuStretch
+    from signalsmith_stretch_b200 import BatchStretch
+
+    x = signals.batch("harmonic", 2, C, n, 48000)
+    g = BatchStretch(2, seed=seed, lib_path=emu_libs["exact"])
+    g.set_tuning(3, 1)
+    cfg(g)
+    y = signals.run_batch(g, x, ratio, chunk)
+    ref = []
+    for s in range(2):
+        o = CpuStretch("orc", seed)
+        cfg(o)
+        ref.append(signals.run_single(o, x[s], ratio, chunk))
+    ref = np.stack(ref)
+    assert np.array_equal(y, ref), "max diff %g" % np.abs(y - ref).max()
+
+
+def test_random_path_mixed_with_clean_calls_bit_exact_vs_oracle(emu_libs):
+    """Calls below and beyond 2x in one stream (the engine state advances only in random blocks; the first block after a
+    ratio change mixes both intervals), a seek at a slow rate (its time factor goes to the next block, :164,:312), and
+    flush with playbackRate 0 (input interval 0, every block random); two streams of one batch where only ONE is silent
+    for a while, so that their schedules -- and their engine states -- diverge."""
+    from oracle.hdrref import CpuStretch
+    from signalsmith_stretch_b200 import BatchStretch
+
+    x = signals.batch("harmonic", 2, 2, 30000, 48000)
+    x[1, :, 6000:16000] = 0  # stream 1 falls silent (bypass after two blocks of silence) while stream 0 keeps stretching
+
+    def seq(o, wrap, unwrap, s):
+        o.configure(2, 512, 128)
+        outs, pos = [], 0
+
+        def run(n_in, n_out):
+            nonlocal pos
+            outs.append(unwrap(o.process(wrap(s[..., pos:pos + n_in]), n_out)))
+            pos += n_in
+
+        run(1024, 1024)
+        run(400, 1280)      # 3.2x
+        run(1024, 1024)     # back to 1x: the first block's interval mixes the two ratios
+        o.seek(wrap(s[..., pos:pos + 700]), 0.3)
+        pos += 700
+        run(600, 1536)      # 2.56x after a seek at rate 0.3
+        run(2000, 2000)
+        run(512, 1536)      # 3x
+        run(3000, 3000)
+        run(3000, 3000)
+        run(640, 1600)
+        outs.append(unwrap(o.flush(900, 0.0)))
+        run(1024, 1024)
+        return np.concatenate(outs, axis=-1)
+
+    g = BatchStretch(2, seed=4242, lib_path=emu_libs["exact"])
+    g.set_tuning(3, 1)
+    y = seq(g, lambda a: a, lambda a: np.array(a), x)  # (copies: the binding reuses its output array)
+    for st in range(2):
+        o = CpuStretch("orc", 4242)
+        r = seq(o, lambda a: a, lambda a: a, x[st])
+        assert np.array_equal(y[st], r), "stream %d: max diff %g" % (st, np.abs(y[st] - r).max())
+
+
 def test_parameters_change_between_calls_bit_exact_vs_oracle(emu_libs, oracle_port):
     """Switching between the kernel paths from call to call -- plain stereo (packed direct chain on interleaved spectra,
     state carried through k_plan / k_commit in both layouts), frequency map (k_prep + generic chain), formants with
