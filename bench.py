@@ -373,6 +373,111 @@ def pcm16_probe(args):
                       "timed": "host wall clock around %d pipelined b200s_process_pcm16() calls + synchronize (int16 host buffers, conversions on the device)" % args.steps}))
 
 
+# ------------------------------------------------------------------------------------ config 5: ratio x preset sweep
+SWEEP_RATIOS = [(2, 1), (3, 2), (5, 4), (1, 1), (4, 5), (2, 3), (1, 2)]  # input / output length: 0.5x ... 2.0x stretch
+SWEEP_BATCH = 4096
+
+
+def algo_bytes_block_channel(B, H, K, in_over_out):
+    """compulsory HBM bytes per block-channel (r = 1 when the previous block is re-analysed)."""
+    h_in = H * in_over_out
+    r = 1 if abs(h_in - H) > 1 else 0
+    return 4 * h_in + 4 * h_in + 4 * B * (1 + r) + 16 * K + 16 * K * (1 - r) + 8 * K + 8 * B + 4 * H
+
+
+def run_sweep(args):
+    """BASELINE configs[4]: stretch ratio 0.5x ... 2.0x  x  {presetDefault, presetCheaper}, batch 4096 mono, one GPU.
+    One JSON line per point (device-resident, CUDA events, 32 blocks per call); not the driver's default run."""
+    import torch
+
+    from signalsmith_stretch_b200 import BatchStretch, build_library
+
+    build_library()
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    global CHANNELS
+    CHANNELS = 1
+    batch = args.batch if args.batch != BATCH_PER_GPU else SWEEP_BATCH
+    for preset in ("presetDefault", "presetCheaper"):
+        for num, den in SWEEP_RATIOS:
+            eng = BatchStretch(batch, device=0)
+            getattr(eng, preset)(1, float(SR))
+            B, H, K = eng.blockSamples(), eng.intervalSamples(), eng.bands()
+            n_out = BLOCKS_PER_STEP * H
+            n_in = n_out * num // den
+            assert n_in * den == n_out * num
+            eng.reserve(n_in, n_out)
+            pool = synth_input(64, 3 * n_in)
+            x = np.tile(pool, ((batch + 63) // 64, 1, 1))[:batch]
+            xd = [torch.from_numpy(np.ascontiguousarray(x[:, :, k * n_in:(k + 1) * n_in])).to(dev) for k in range(3)]
+            yd = torch.empty((batch, 1, n_out), dtype=torch.float32, device=dev)
+            for i in range(max(args.warmup, 3)):
+                eng.process(xd[i % 3], n_out, out=yd)
+            eng.synchronize()
+            eng.timer_start()
+            for i in range(args.steps):
+                eng.process(xd[i % 3], n_out, out=yd)
+            ms = eng.timer_stop() / args.steps
+            eng.profile_begin()
+            for i in range(2):
+                eng.process(xd[i % 3], n_out, out=yd)
+            prof = eng.profile_end()
+            kern = {k: v[0] / max(v[1], 1) for k, v in prof.items()}
+            unserved = eng.unserved_random_blocks()
+            algo = algo_bytes_block_channel(B, H, K, num / den)
+            achieved = algo * batch * BLOCKS_PER_STEP / (ms * 1e-3) / 1e9
+            print(json.dumps({
+                "metric": METRIC, "value": batch * n_out / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
+                "ms_per_step": ms, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[4] sweep point: batch=%d mono 48 kHz %s, input/output = %d/%d (%.3gx stretch)"
+                                       % (batch, preset, num, den, den / num),
+                           "preset": preset, "in_over_out": num / den, "block": B, "interval": H, "bands": K, "blocks_per_step": BLOCKS_PER_STEP},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "algo_bytes_per_block_channel": algo, "algo_bytes_per_output_sample": algo / H, "kernel_ms_per_step": kern},
+                "unserved_random_blocks": unserved}), flush=True)
+            del eng, xd, yd
+            torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------ live / streaming caller
+def run_live(args):
+    """the reference's live wrapper (web/web-wrapper.js:215-332: seek + process(0, 128) per audio
+    quantum) as a batched server loop (signalsmith_stretch_b200/live.py), batch 1024 stereo, every stream its own rate.
+    Host wall clock: the loop includes the per-quantum window gathering on the host, like the worklet's."""
+    import torch
+
+    from signalsmith_stretch_b200 import BatchStretch, build_library
+    from signalsmith_stretch_b200.live import LiveBatch
+
+    build_library()
+    torch.cuda.set_device(0)
+    batch, quantum = args.batch, 128
+    eng = BatchStretch(batch, device=0)
+    eng.presetDefault(CHANNELS, float(SR))
+    live = LiveBatch(eng, float(SR))
+    pool = synth_input(64, 4 * SR)
+    for s in range(batch):
+        live.add_buffers(s, pool[s % 64])
+        live.start(s, when=0.0, offset=0.05 * (s % 7), rate=0.6 + 0.1 * (s % 9))
+    for _ in range(20):
+        live.process(quantum)
+    eng.synchronize()
+    n = max(args.steps, 10) * 20
+    t0 = time.perf_counter()
+    t_gpu = 0.0
+    for _ in range(n):
+        live.process(quantum)
+    eng.synchronize()
+    dt = time.perf_counter() - t0
+    print(json.dumps({"metric": "live quanta/s (seek + process(0, 128) per quantum for every stream)", "value": n / dt, "unit": "quanta/s",
+                      "streams": batch, "channels": CHANNELS, "quantum": quantum, "stream_quanta_per_s": n * batch / dt,
+                      "realtime_streams_sustained": n * batch / dt / (SR / quantum),
+                      "output_samples_per_s_per_channel": n * batch * CHANNELS * quantum / dt, "ms_per_quantum": dt / n * 1e3,
+                      "timed": "host wall clock over %d quanta incl. the host-side window gathering, H2D of the seek windows and D2H of the output" % n}))
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -384,11 +489,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs (ncu): device-resident steps only; the JSON line then has no e2e / per-kernel split")
     ap.add_argument("--sub-batches", type=int, default=0, help="device-resident path: split the batch over N prioritised CUDA streams (experiment)")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4], help="BASELINE config (default 2 = the headline)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE config (default 2 = the headline; 5 = the ratio x preset sweep, one line per point)")
     ap.add_argument("--pcm16-probe", action="store_true", help="internal: child process measuring the 16-bit PCM boundary")
+    ap.add_argument("--live", action="store_true", help="the live / streaming caller (seek + process(0, 128) per quantum), batch 1024 stereo")
     args = ap.parse_args()
     if args.pcm16_probe:
         pcm16_probe(args)
+        return
+    if args.live:
+        run_live(args)
+        return
+    if args.config == 5:
+        run_sweep(args)
         return
     if args.config != 2:
         global CHANNELS, RATIO_OUT, ALGO_BYTES_PER_BLOCK_CHANNEL

@@ -96,6 +96,10 @@ int b200s_set_freq_map_table(b200s_engine *e, const float *freq_in, const float 
  * Host-buffer variants: `in`/`out` are host pointers, planar [batch][channels][samples]; the call
  * copies host->device, runs, copies device->host and synchronises. */
 int b200s_seek(b200s_engine *e, const float *in, int input_samples, double playback_rate);
+/* seek() with one playback rate per stream (`playback_rates[batch]`): what a server needs whose streams follow their own
+ * time maps (the reference's live wrapper seeks every audio quantum with the current segment's rate,
+ * web/web-wrapper.js:314-315); signalsmith_stretch_b200/live.py is that loop for a batch. */
+int b200s_seek_rates(b200s_engine *e, const float *in, int input_samples, const double *playback_rates);
 int b200s_output_seek(b200s_engine *e, const float *in, int input_length);
 int b200s_process(b200s_engine *e, const float *in, int input_samples, float *out, int output_samples);
 /* As b200s_process(), but returns as soon as the copies and kernels are enqueued: consecutive calls pipeline (stream

@@ -49,6 +49,10 @@ struct b200s_engine {
 	int exactMath = 0;         // b200s_set_tuning key 3: 1 = the phase chain in the reference's unfused IEEE arithmetic
 	int nHostParts = 12; // (measured, batch 1024 stereo: 2 -> 15.1, 4 -> 13.0, 8 -> 12.2, 12 -> 11.2, 16 -> 11.8 ms per step) host-buffer API: stream groups whose H2D copy / kernels / D2H copy are pipelined
 	cudaEvent_t evStart = 0, evStop = 0;
+	// k_commit (state carry + history append) only needs the chain's output, not the synthesis: it runs on a side stream
+	// beside k_synth2 (fork after the chain, join after both)
+	cudaStream_t commitStream = 0;
+	cudaEvent_t evFork = 0, evJoin = 0;
 	long long launches = 0, allocs = 0;
 	std::string err;
 	// optional per-kernel CUDA-event timing (b200s_profile_begin/end)
@@ -82,6 +86,8 @@ struct b200s_engine {
 	// reference's randomEngine member), powers of the multiplier, the upwards twists of random blocks
 	unsigned *dRng = 0, *dRngPow = 0;
 	unsigned long long *dDiag = 0;
+	float *dSeekStf = 0; // per-stream seek time factors (b200s_seek_rates)
+	std::vector<float> hSeekStf;
 	unsigned rngJump = 1;
 	float2 *dT1u = 0, *dT2u = 0;
 	int randFrames = 0;
@@ -307,8 +313,9 @@ static ChainKernel chain_kernel(const Cfg &g, bool direct) {
 	return g.C == 1 ? chain_kernel_for<1>(g.L, direct) : chain_kernel_for<2>(g.L, direct);
 }
 static const int kChainWarps = 1; // one stream per CTA: 1024 streams spread evenly over the 148 SMs
-static size_t smem_chain(const Cfg &g, bool direct) {
+static size_t smem_chain(const Cfg &g, bool direct, bool randTiles = false) {
 	size_t per = direct ? (g.C == 1 ? sizeof(DirectTiles2<1>) : sizeof(DirectTiles2<2>)) : (g.C == 1 ? sizeof(ChainTiles<1>) : sizeof(ChainTiles<2>));
+	if (!direct && randTiles) per += g.C == 1 ? sizeof(ChainRandTiles<1>) : sizeof(ChainRandTiles<2>);
 	return per * kChainWarps;
 }
 
@@ -505,7 +512,7 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	CK(cudaFuncSetAttribute(k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_prep(g)));
 	CK(cudaFuncSetAttribute(synth_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_synth(g)));
 	CK(cudaFuncSetAttribute(k_flush_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * g.B)));
-	CK(cudaFuncSetAttribute(chain_kernel(g, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, false)));
+	CK(cudaFuncSetAttribute(chain_kernel(g, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, false, true)));
 	CK(cudaFuncSetAttribute(chain_kernel(g, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, true)));
 	CK(cudaFuncSetAttribute(chain2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain2(g.C, CH2_MAXW)));
 	if (g.L <= 4) { // seven two-warp CTAs of 30.6 KB per SM: ask for the full shared-memory carve-out
@@ -714,7 +721,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 				} else {
 					dim3 grid((x.sCount + kChainWarps - 1) / kChainWarps), block(32 * kChainWarps);
 					ChainKernel kc = chain_kernel(g, plain);
-					PROF(PK_CHAIN, B200S_LAUNCH(kc, grid, block, smem_chain(g, plain), st, x));
+					PROF(PK_CHAIN, B200S_LAUNCH(kc, grid, block, smem_chain(g, plain, mayRandom), st, x));
 				}
 			}
 			if (F > 0 && plain && mayRandom) {
@@ -726,9 +733,16 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 				CKL();
 				dim3 grid((x.sCount + kChainWarps - 1) / kChainWarps), block(32 * kChainWarps);
 				ChainKernel kc = chain_kernel(g, false);
-				B200S_LAUNCH(kc, grid, block, smem_chain(g, false), st, x);
+				B200S_LAUNCH(kc, grid, block, smem_chain(g, false, true), st, x);
 				CKL();
 				x.randomOnly = 0;
+			}
+			// fork: the commit of this call runs beside the synthesis (both only read what the chain wrote)
+			const bool forkCommit = nSub == 1 && !e->profiling && e->commitStream;
+			cudaStream_t cst = forkCommit ? e->commitStream : st;
+			if (forkCommit) {
+				CK(cudaEventRecord(e->evFork, st));
+				CK(cudaStreamWaitEvent(cst, e->evFork, 0));
 			}
 			if (pairFft) {
 				PROF(PK_SYNTH, B200S_LAUNCH(synth2_kernel(g), dim3(g.C, x.sCount), dim3(256), smem_synth2(g), st, x));
@@ -737,7 +751,11 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 				PROF(PK_SYNTH, B200S_LAUNCH(ks, dim3(g.C, x.sCount), dim3(kThreads), smem_synth(g), st, x));
 			}
 			// (measured: folding the commit into k_synth2's CTAs costs more there than the launch saves: 4.76 vs 4.68 ms)
-			PROF(PK_COMMIT, B200S_LAUNCH(k_commit, dim3(g.C, x.sCount), dim3(kThreads), 0, st, x));
+			PROF(PK_COMMIT, B200S_LAUNCH(k_commit, dim3(g.C, x.sCount), dim3(kThreads), 0, cst, x));
+			if (forkCommit) {
+				CK(cudaEventRecord(e->evJoin, cst));
+				CK(cudaStreamWaitEvent(st, e->evJoin, 0));
+			}
 		}
 		if (hOut && nOut > 0)
 			CK(cudaMemcpyAsync(hOut + (size_t)x.sBase * g.C * nOut, dOut + (size_t)x.sBase * g.C * nOut, sizeof(float) * (size_t)x.sCount * g.C * nOut, cudaMemcpyDeviceToHost, st));
@@ -756,13 +774,25 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	return 0;
 }
 
-static int seek_impl(b200s_engine *e, const float *dIn, int chanStride, long long streamStride, int n, double playbackRate) {
+static int seek_impl(b200s_engine *e, const float *dIn, int chanStride, long long streamStride, int n, double playbackRate, const double *rates = nullptr) {
 	const Cfg &g = e->cfg;
 	e->chainedGroups = 0;
 	Ctx x = make_ctx(e);
 	x.in = dIn; x.nIn = n; x.inChanStride = chanStride; x.inStreamStride = streamStride;
 	float stf = (playbackRate * g.H > 1) ? float(1 / playbackRate) : float(g.H); // :164
 	e->seekMayRandom = stf > 1.9f; // the next block takes this as its time factor (:312)
+	if (rates) { // one playback rate per stream (a server whose streams follow their own time maps)
+		int rc;
+		if (!e->dSeekStf && (rc = dalloc(e, &e->dSeekStf, (size_t)g.S))) return rc;
+		e->hSeekStf.resize(g.S);
+		e->seekMayRandom = false;
+		for (int s = 0; s < g.S; ++s) {
+			e->hSeekStf[s] = (rates[s] * g.H > 1) ? float(1 / rates[s]) : float(g.H);
+			if (e->hSeekStf[s] > 1.9f) e->seekMayRandom = true;
+		}
+		CK(cudaMemcpyAsync(e->dSeekStf, e->hSeekStf.data(), sizeof(float) * g.S, cudaMemcpyHostToDevice, e->stream));
+		x.seekStf = e->dSeekStf;
+	}
 	B200S_LAUNCH(k_seek, dim3(g.S), dim3(kThreads), 0, e->stream, x, stf);
 	CKL();
 	return 0;
@@ -858,6 +888,14 @@ int b200s_create(int batch, long seed, int device, b200s_engine **out) {
 		return B200S_ECUDA;
 	}
 	e->ownStream = true;
+	{
+		int lo = 0, hi = 0;
+		cudaDeviceGetStreamPriorityRange(&lo, &hi);
+		if (cudaStreamCreateWithPriority(&e->commitStream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&e->evJoin, cudaEventDisableTiming) != cudaSuccess)
+			e->commitStream = 0; // (no fork then: the commit follows the synthesis on the main stream)
+	}
 	{ // sub-batch streams: highest priority first
 		int lo = 0, hi = 0;
 		cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -888,11 +926,15 @@ void b200s_destroy(b200s_engine *e) {
 	dfree(e->dMapOut);
 	dfree(e->dRng);
 	dfree(e->dDiag);
+	dfree(e->dSeekStf);
 	for (int i = 0; i < b200s_engine::kMaxSub; ++i) {
 		if (e->subStream[i]) cudaStreamDestroy(e->subStream[i]);
 		if (e->evSubDone[i]) cudaEventDestroy(e->evSubDone[i]);
 	}
 	if (e->evBegin) cudaEventDestroy(e->evBegin);
+	if (e->commitStream) cudaStreamDestroy(e->commitStream);
+	if (e->evFork) cudaEventDestroy(e->evFork);
+	if (e->evJoin) cudaEventDestroy(e->evJoin);
 	if (e->evStart) cudaEventDestroy(e->evStart);
 	if (e->evStop) cudaEventDestroy(e->evStop);
 	if (e->ownStream && e->stream) cudaStreamDestroy(e->stream);
@@ -1035,6 +1077,15 @@ int b200s_seek(b200s_engine *e, const float *in, int n, double rate) {
 	int rc;
 	if ((rc = stage_in(e, in, n))) return rc;
 	if ((rc = seek_impl(e, e->dIn, n, (long long)e->cfg.C * n, n, rate))) return rc;
+	CK(cudaStreamSynchronize(e->stream));
+	return 0;
+}
+int b200s_seek_rates(b200s_engine *e, const float *in, int n, const double *rates) {
+	NEED_CFG();
+	if (n < 0 || !rates) return B200S_EINVAL;
+	int rc;
+	if ((rc = stage_in(e, in, n))) return rc;
+	if ((rc = seek_impl(e, e->dIn, n, (long long)e->cfg.C * n, n, 1.0, rates))) return rc;
 	CK(cudaStreamSynchronize(e->stream));
 	return 0;
 }

@@ -658,3 +658,84 @@ print("ok")
     for p in procs:
         out, err = p.communicate(timeout=120)
         assert p.returncode == 0 and "ok" in out, err
+
+
+# ------------------------------------------------------------------ the live / streaming caller (web/web-wrapper.js:215-332)
+class _OneStream:
+    """Adapter: a one-stream oracle object behind the BatchStretch calls LiveBatch makes (batch of 1)."""
+
+    def __init__(self, o):
+        self.o, self.batch = o, 1
+
+    def channels(self):
+        return self.o.channels
+
+    def inputLatency(self):
+        return self.o.inputLatency()
+
+    def outputLatency(self):
+        return self.o.outputLatency()
+
+    def seek(self, win, rates):
+        self.o.seek(win[0], float(rates[0]))
+
+    def process(self, x, n_out):
+        return self.o.process(x[0], n_out)[None]
+
+
+def test_live_batch_seek_every_quantum_bit_exact_vs_oracle(emu_libs, oracle_port):
+    """the reference's live wrapper seeks every audio quantum with the current time-map
+    segment's rate and renders `process(0, quantum)` (web-wrapper.js:314-315).  LiveBatch does that for a batch with
+    one b200s_seek_rates + one b200s_process per quantum; three streams with their own rates / offsets / loop / stop
+    times against three oracle objects driven by the same loop, bit for bit."""
+    from signalsmith_stretch_b200.live import LiveBatch
+
+    sr, S, C, quantum = 48000.0, 3, 2, 128
+    audio = signals.batch("harmonic", S, C, 12000, 48000)
+    g = _emu(emu_libs["exact"], S)
+    g.configure(C, 512, 128)
+    live = LiveBatch(g, sr)
+    refs = []
+    for s in range(S):
+        o = oracle_port()
+        o.configure(C, 512, 128)
+        refs.append(LiveBatch(_OneStream(o), sr))
+
+    def both(fn):
+        fn(live, lambda s: s)
+        for s, r in enumerate(refs):
+            fn(r, lambda _s, s=s: 0 if _s == s else None)
+
+    def setup(lv, idx):
+        for s in range(S):
+            i = idx(s)
+            if i is None:
+                continue
+            lv.add_buffers(i, audio[s])
+        for s, kw in enumerate([dict(rate=0.8, offset=0.01), dict(rate=1.0, offset=0.0), dict(rate=1.3, offset=0.02)]):
+            i = idx(s)
+            if i is not None:
+                lv.start(i, when=0.004 * s, **kw)
+        i = idx(2)
+        if i is not None:  # stream 2 loops between 50 ms and 110 ms of its input
+            lv.schedule(i, dict(outputTime=0.03, loopStart=0.05, loopEnd=0.11), adjust_previous=False)
+
+    both(setup)
+    outs, ref_outs = [], [[] for _ in range(S)]
+    for qn in range(40):
+        if qn == 25:  # stream 0 stops; stream 1 slows down now and is steered to input 0.1 s at output 0.2 s (adjustPrevious)
+            both(lambda lv, idx: [lv.stop(idx(0)) if idx(0) is not None else None,
+                                  lv.schedule(idx(1), dict(rate=0.6)) if idx(1) is not None else None,
+                                  lv.schedule(idx(1), dict(outputTime=0.2, input=0.1), adjust_previous=True) if idx(1) is not None else None])
+        outs.append(live.process(quantum))
+        for s, r in enumerate(refs):
+            ref_outs[s].append(r.process(quantum)[0])
+    y = np.concatenate(outs, axis=-1)
+    for s in range(S):
+        r = np.concatenate(ref_outs[s], axis=-1)
+        if s == 0:  # the stopped stream: compared while it plays (documented difference of a batch call afterwards)
+            n = 25 * quantum
+            assert np.array_equal(y[s][:, :n], r[:, :n]), "stream 0: max diff %g" % np.abs(y[s][:, :n] - r[:, :n]).max()
+        else:
+            assert np.array_equal(y[s], r), "stream %d: max diff %g" % (s, np.abs(y[s] - r).max())
+    assert np.abs(y).max() > 0.05
