@@ -491,6 +491,7 @@ def main():
     ap.add_argument("--sub-batches", type=int, default=0, help="device-resident path: split the batch over N prioritised CUDA streams (experiment)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE config (default 2 = the headline; 5 = the ratio x preset sweep, one line per point)")
     ap.add_argument("--pcm16-probe", action="store_true", help="internal: child process measuring the 16-bit PCM boundary")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the child runs of BASELINE configs[2] / [3]")
     ap.add_argument("--live", action="store_true", help="the live / streaming caller (seek + process(0, 128) per quantum), batch 1024 stereo")
     args = ap.parse_args()
     if args.pcm16_probe:
@@ -577,8 +578,14 @@ def main():
 
     if args.no_e2e:
         if rank == 0:
+            pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            pkv = float(json.load(open(pk))["hbm_gbs"]) if os.path.exists(pk) else 6650.0
+            ach = ALGO_BYTES_PER_BLOCK_CHANNEL * args.batch * CHANNELS * BLOCKS_PER_STEP / (tmax / args.steps) / 1e9
             print(json.dumps({"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-                              "ms_per_step": tmax / args.steps * 1e3, "gpu_launches": int(launches), "note": "--no-e2e profiling run"}))
+                              "ms_per_step": tmax / args.steps * 1e3, "gpu_launches": int(launches),
+                              "roofline_frac": ach / pkv, "algo_bytes_per_block_channel": ALGO_BYTES_PER_BLOCK_CHANNEL,
+                              "workload": EXTRA[args.config]["name"] if args.config in EXTRA else "BASELINE configs[1]",
+                              "note": "--no-e2e run (device-resident only)"}))
         if world > 1:
             dist.destroy_process_group()
         return
@@ -668,13 +675,26 @@ def main():
         except Exception as ex:  # noqa: BLE001
             e2e_pcm16 = {"unavailable": str(ex)[-200:]}
 
+    # BASELINE configs[2] / [3] (frequency map; formants) on this GPU, device-resident, in child processes: reported beside
+    # the headline (never instead of it) so that the driver's record carries them too
+    other_configs = None
+    if rank == 0 and world == 1 and args.config == 2 and not args.no_other_configs:
+        other_configs = {}
+        for c in (3, 4):
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", str(c), "--steps", "5", "--no-e2e"],
+                                   capture_output=True, text=True, timeout=240)
+                other_configs["config%d" % c] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"unavailable": (r.stderr or "failed")[-200:]}
+            except Exception as ex:  # noqa: BLE001
+                other_configs["config%d" % c] = {"unavailable": str(ex)[-200:]}
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tmax / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": dict(config_dict(w, world), **({} if args.config == 2 else {"workload": EXTRA[args.config]["name"]})), "clocks": clk,
-            "e2e": e2e, "e2e_pcm16": e2e_pcm16, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}))
+            "e2e": e2e, "e2e_pcm16": e2e_pcm16, "other_configs": other_configs, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -100,6 +100,11 @@ int b200s_seek(b200s_engine *e, const float *in, int input_samples, double playb
  * time maps (the reference's live wrapper seeks every audio quantum with the current segment's rate,
  * web/web-wrapper.js:314-315); signalsmith_stretch_b200/live.py is that loop for a batch. */
 int b200s_seek_rates(b200s_engine *e, const float *in, int input_samples, const double *playback_rates);
+/* The live loop without the per-quantum upload: the streams' audio sits in a DEVICE bank [batch][channels][bank_len]
+ * (uploaded once); every quantum only the `batch` window positions and rates cross PCIe.  Stream s seeks with the `window`
+ * samples that end at bank index window_end[s] (host array; samples outside [0, bank_len) read as zero -- the worklet's zero
+ * padding, web-wrapper.js:289-311), at playback_rates[s] (host array).  Asynchronous on the handle's stream. */
+int b200s_live_seek(b200s_engine *e, const float *d_bank, long long bank_len, const long long *window_end, int window, const double *playback_rates);
 int b200s_output_seek(b200s_engine *e, const float *in, int input_length);
 int b200s_process(b200s_engine *e, const float *in, int input_samples, float *out, int output_samples);
 /* As b200s_process(), but returns as soon as the copies and kernels are enqueued: consecutive calls pipeline (stream

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "b200s_fft_samples", "b200s_bands",
     "b200s_set_transpose_factor", "b200s_set_transpose_semitones", "b200s_set_formant_factor",
     "b200s_set_formant_semitones", "b200s_set_formant_base", "b200s_set_freq_map_table",
-    "b200s_seek", "b200s_seek_rates", "b200s_output_seek", "b200s_process", "b200s_process_async", "b200s_process_pcm16", "b200s_flush", "b200s_exact",
+    "b200s_seek", "b200s_seek_rates", "b200s_live_seek", "b200s_output_seek", "b200s_process", "b200s_process_async", "b200s_process_pcm16", "b200s_flush", "b200s_exact",
     "b200s_seek_device", "b200s_process_device", "b200s_flush_device",
     "b200s_timer_start", "b200s_timer_stop", "b200s_kernel_launches", "b200s_device_allocations", "b200s_unserved_random_blocks", "b200s_profile_begin", "b200s_profile_end",
     "b200s_selftest_divsqrt",
@@ -81,7 +81,7 @@ def _bind(lib):
         "b200s_set_transpose_factor": (ci, [vp, cf, cf]), "b200s_set_transpose_semitones": (ci, [vp, cf, cf]),
         "b200s_set_formant_factor": (ci, [vp, cf, ci]), "b200s_set_formant_semitones": (ci, [vp, cf, ci]),
         "b200s_set_formant_base": (ci, [vp, cf]), "b200s_set_freq_map_table": (ci, [vp, fp, fp, ci]),
-        "b200s_seek": (ci, [vp, vp, ci, cd]), "b200s_seek_rates": (ci, [vp, vp, ci, ctypes.POINTER(cd)]), "b200s_output_seek": (ci, [vp, vp, ci]),
+        "b200s_seek": (ci, [vp, vp, ci, cd]), "b200s_seek_rates": (ci, [vp, vp, ci, ctypes.POINTER(cd)]), "b200s_live_seek": (ci, [vp, vp, cll, ctypes.POINTER(cll), ci, ctypes.POINTER(cd)]), "b200s_output_seek": (ci, [vp, vp, ci]),
         "b200s_process": (ci, [vp, vp, ci, vp, ci]), "b200s_process_async": (ci, [vp, vp, ci, vp, ci]), "b200s_process_pcm16": (ci, [vp, vp, ci, vp, ci, ci]), "b200s_flush": (ci, [vp, vp, ci, cf]),
         "b200s_exact": (ci, [vp, vp, ci, vp, ci, ip]),
         "b200s_seek_device": (ci, [vp, vp, ci, cd]), "b200s_process_device": (ci, [vp, vp, ci, vp, ci]),
@@ -252,6 +252,15 @@ class BatchStretch:
             self._ck(self._lib.b200s_seek_rates(self._h, x.ctypes.data, n, r.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
             return
         self._ck(self._lib.b200s_seek(self._h, x.ctypes.data, n, float(playbackRate)))
+
+    def live_seek(self, bank_ptr, bank_len, window_end, window, rates):
+        """b200s_live_seek: seek windows cut from a device-resident audio bank (pointer), one end index and rate per stream."""
+        we = np.ascontiguousarray(window_end, np.int64)
+        r = np.ascontiguousarray(rates, np.float64)
+        if we.shape != (self.batch,) or r.shape != (self.batch,):
+            raise ValueError("expected %d window ends and rates" % self.batch)
+        self._ck(self._lib.b200s_live_seek(self._h, ctypes.c_void_p(int(bank_ptr)), int(bank_len), we.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)),
+                                           int(window), r.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
 
     def outputSeek(self, inputs):
         x = np.asarray(inputs, np.float32)

@@ -136,6 +136,8 @@ struct Ctx {
 	unsigned *rngState;     // [S] engine state per stream (persists over reset / configure, like the reference's member)
 	const unsigned *rngPow; // [2K] 16807^i mod 2^31-1
 	unsigned rngJump;       // 16807^(2K-2): one block's worth of draws
+	const long long *seekEnd; // k_seek from a device-resident audio bank (b200s_live_seek): per stream, the bank index at which the
+	long long bankLen;        // seek window ends; samples outside [0, bankLen) read as zero.  Null: x.in holds the window itself
 	const float *seekStf;   // k_seek: per-stream seekTimeFactor (b200s_seek_rates), or null: the launch argument for every stream
 	int randomPathOn;       // the kernels of the random path run in this call: the direct chain kernels leave hasRandom streams to them
 	unsigned long long *diag; // [1] blocks whose random time factors could not be honoured (random path not launched; see engine.cu)

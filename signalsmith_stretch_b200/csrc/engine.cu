@@ -88,6 +88,7 @@ struct b200s_engine {
 	unsigned long long *dDiag = 0;
 	float *dSeekStf = 0; // per-stream seek time factors (b200s_seek_rates)
 	std::vector<float> hSeekStf;
+	long long *dSeekEnd = 0; // per-stream window ends in the audio bank (b200s_live_seek)
 	unsigned rngJump = 1;
 	float2 *dT1u = 0, *dT2u = 0;
 	int randFrames = 0;
@@ -774,11 +775,19 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	return 0;
 }
 
-static int seek_impl(b200s_engine *e, const float *dIn, int chanStride, long long streamStride, int n, double playbackRate, const double *rates = nullptr) {
+static int seek_impl(b200s_engine *e, const float *dIn, int chanStride, long long streamStride, int n, double playbackRate, const double *rates = nullptr,
+                     const long long *bankEnds = nullptr, long long bankLen = 0) {
 	const Cfg &g = e->cfg;
 	e->chainedGroups = 0;
 	Ctx x = make_ctx(e);
 	x.in = dIn; x.nIn = n; x.inChanStride = chanStride; x.inStreamStride = streamStride;
+	if (bankEnds) { // the windows are cut out of a device-resident audio bank by k_seek itself
+		int rc;
+		if (!e->dSeekEnd && (rc = dalloc(e, &e->dSeekEnd, (size_t)g.S))) return rc;
+		CK(cudaMemcpyAsync(e->dSeekEnd, bankEnds, sizeof(long long) * g.S, cudaMemcpyHostToDevice, e->stream));
+		x.seekEnd = e->dSeekEnd;
+		x.bankLen = bankLen;
+	}
 	float stf = (playbackRate * g.H > 1) ? float(1 / playbackRate) : float(g.H); // :164
 	e->seekMayRandom = stf > 1.9f; // the next block takes this as its time factor (:312)
 	if (rates) { // one playback rate per stream (a server whose streams follow their own time maps)
@@ -927,6 +936,7 @@ void b200s_destroy(b200s_engine *e) {
 	dfree(e->dRng);
 	dfree(e->dDiag);
 	dfree(e->dSeekStf);
+	dfree(e->dSeekEnd);
 	for (int i = 0; i < b200s_engine::kMaxSub; ++i) {
 		if (e->subStream[i]) cudaStreamDestroy(e->subStream[i]);
 		if (e->evSubDone[i]) cudaEventDestroy(e->evSubDone[i]);
@@ -1088,6 +1098,15 @@ int b200s_seek_rates(b200s_engine *e, const float *in, int n, const double *rate
 	if ((rc = seek_impl(e, e->dIn, n, (long long)e->cfg.C * n, n, 1.0, rates))) return rc;
 	CK(cudaStreamSynchronize(e->stream));
 	return 0;
+}
+int b200s_live_seek(b200s_engine *e, const float *d_bank, long long bank_len, const long long *window_end, int window, const double *rates) {
+	NEED_CFG();
+	if (window < 0 || bank_len < 0 || !d_bank || !window_end || !rates) return B200S_EINVAL;
+	if (bank_len > 0x7fffffffLL) {
+		e->err = "b200s_live_seek: bank rows longer than 2^31-1 samples are not supported";
+		return B200S_EUNSUPPORTED;
+	}
+	return seek_impl(e, d_bank, (int)bank_len, (long long)e->cfg.C * bank_len, window, 1.0, rates, window_end, bank_len);
 }
 int b200s_process(b200s_engine *e, const float *in, int nIn, float *out, int nOut) {
 	NEED_CFG();

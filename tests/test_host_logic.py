@@ -683,7 +683,8 @@ class _OneStream:
         return self.o.process(x[0], n_out)[None]
 
 
-def test_live_batch_seek_every_quantum_bit_exact_vs_oracle(emu_libs, oracle_port):
+@pytest.mark.parametrize("bank", [None, "numpy"], ids=["host_windows", "device_bank"])
+def test_live_batch_seek_every_quantum_bit_exact_vs_oracle(emu_libs, oracle_port, bank):
     """the reference's live wrapper seeks every audio quantum with the current time-map
     segment's rate and renders `process(0, quantum)` (web-wrapper.js:314-315).  LiveBatch does that for a batch with
     one b200s_seek_rates + one b200s_process per quantum; three streams with their own rates / offsets / loop / stop
@@ -694,7 +695,9 @@ def test_live_batch_seek_every_quantum_bit_exact_vs_oracle(emu_libs, oracle_port
     audio = signals.batch("harmonic", S, C, 12000, 48000)
     g = _emu(emu_libs["exact"], S)
     g.configure(C, 512, 128)
-    live = LiveBatch(g, sr)
+    # bank: the streams' audio in a "device" bank (host memory under the emulator), windows cut by the seek kernel
+    # (b200s_live_seek); None: windows gathered on the host and uploaded (b200s_seek_rates)
+    live = LiveBatch(g, sr, bank=bank)
     refs = []
     for s in range(S):
         o = oracle_port()
