@@ -1,0 +1,311 @@
+// chain_t.cuh -- k_products + k_chain_t: the frequency-mapped / formant configurations with the chain-independent terms
+// handed to the chain in STEP-MAJOR order (round 2).
+//
+// The generic path of round 1 (k_prep -> coefficient rows [block][bin] -> k_chain) made the chain warp turn rows into
+// columns: per chunk of 8 steps every lane needs 8 bins of ITS OWN block's five coefficient rows, i.e. 40-80 small
+// cp.async per lane, staged through [step][lane] shared-memory tiles, waited for before the chunk could start
+// (profiles/r02_config3_ncu_summary.md: 1950 cycles per step, long_scoreboard 2.0 cycles per instruction).
+// Here the transposition happens once, in a throughput kernel:
+//   * k_prep (map-only mode) stops after the serial-free part that needs a whole block in shared memory -- peaks,
+//     output map, formant ratio -- and writes 12 B per bin: mapBin, mapGrad, ratio rows.
+//   * k_products (grid: 32-step chunks x 32-block groups x streams) evaluates, per (block j, bin q), exactly what
+//     k_prep's last stage evaluates -- Prediction::energy / input, freqTwist, the short and long vertical twists
+//     (:696-719,:750-758) -- with lanes along the BINS of one block (the gathers at the mapped positions are then
+//     nearly contiguous), collects a [32 steps][32 blocks] tile per quantity in shared memory and writes it out as rows
+//     of 32 lanes: element (j, q) of every quantity lands at row k = (the step at which lane j consumes it), so
+//     FT / T2 / E at k = q + D j, T1 at k = q + L - 1 + D j, PI at k = q + L + D j   (D = L + 1, the lane skew).
+//   * k_chain_t (one warp per stream, lane = block, as k_chain) reads ROW k of every array at step k: five coalesced
+//     128 / 256-byte loads per channel, next step's already in flight, no shared-memory staging, no index arithmetic.
+// Arithmetic is the exact (unfused IEEE) arithmetic of k_prep / k_chain, operation for operation: the emulator tests
+// compare it with the oracle bit for bit.  Streams with a random block (beyond 2x stretch) keep the round-1 kernels.
+#pragma once
+#include "kernels.cuh"
+
+namespace b200s {
+
+__host__ __device__ __forceinline__ int t_rows(const Cfg &g) { return ((g.K + g.L + (g.L + 1) * 31 + 1) + 31) & ~31; } // steps of a group, padded to 32
+__device__ __forceinline__ size_t t_idx(const Ctx &x, int s, int grp, int k, int c, int lane) {
+	return ((((size_t)s * x.tGroups + grp) * x.tRows + k) * x.cfg.C + c) * 32 + lane;
+}
+
+__global__ void __launch_bounds__(256) k_products(Ctx x) {
+	const Cfg &g = x.cfg;
+	const Params &prm = x.prm;
+	const int K = g.K, LT = g.L, D = LT + 1;
+	const int k0 = blockIdx.x * 32, grp = blockIdx.y, s = x.sBase + blockIdx.z;
+	const int i = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const Call cl = x.call[s];
+	const int base = 32 * grp, nAct = min(32, cl.nFrames - base);
+	if (cl.bypass || nAct <= 0 || (cl.hasRandom && x.randomPathOn)) return;
+	B200S_SHARED float2 tFT[32][33], tT2[32][33], tT1[32][33], tPI[32][33];
+	B200S_SHARED float tE[32][33];
+	for (int c = 0; c < g.C; ++c) {
+		for (int j = w; j < 32; j += 8) {
+			float2 ft = make_float2(0.f, 0.f), t1 = ft, t2 = ft, pin = ft;
+			float e = 0.f;
+			const int q = k0 + i - D * j;
+			if (j < nAct && q >= 0 && q < K) {
+				const int f = base + j;
+				const Frame fr = x.frames[(size_t)s * x.maxFrames + f];
+				const bool mapped = fr.flags & FR_MAPPED, formants = fr.flags & FR_FORMANTS, rotOn = fr.flags & FR_NEW_SPECTRUM;
+				const size_t row = ((size_t)s * x.maxFrames + f) * K;
+				const float tf = fmaxf(fr.timeFactor, 1.0f / B200S_MAX_CLEAN_STRETCH); // :638
+				const float longTf = fmul((float)LT, tf);
+				auto gin = [&](int b) { return (b < 0 || b >= K) ? make_float2(0.f, 0.f) : spec_val(x, s, fr.inSlot, c, b); };
+				auto gpv = [&](int b) { // prevInput is rotated in place before being interpolated (:654)
+					if (b < 0 || b >= K) return make_float2(0.f, 0.f);
+					const float2 v = spec_val(x, s, fr.prevSlot, c, b);
+					return rotOn ? xmul(v, __ldg(x.rot + b)) : v;
+				};
+				const float mb = mapped ? x.cMapB[row + q] : (float)q;
+				const float mg = mapped ? x.cMapG[row + q] : 1.f;
+				const int lo = (int)floorf(mb);
+				const float frac = fsub(mb, (float)lo);
+				const float2 inLo = gin(lo), inHi = gin(lo + 1);
+				float eLo = xnorm(inLo), eHi = xnorm(inHi); // Band::inputEnergy (:679,:826)
+				if (formants) {
+					if (lo >= 0 && lo < K) eLo = fmul(eLo, x.cRatio[row + lo]);
+					if (lo + 1 >= 0 && lo + 1 < K) eHi = fmul(eHi, x.cRatio[row + lo + 1]);
+				}
+				e = fmul(xlerp(eLo, eHi, frac), fmaxf(0.f, mg)); // :708-709
+				pin = xlerp2(inLo, inHi, frac);                  // :710
+				const float2 pprev = xlerp2(gpv(lo), gpv(lo + 1), frac); // :713
+				ft = xmulc(pin, pprev);                          // :714
+				const float i1 = fsub(mb, tf); // :750-751
+				const int l1 = (int)floorf(i1);
+				t1 = xmulc(pin, xlerp2(gin(l1), gin(l1 + 1), fsub(i1, (float)l1)));
+				const float i2 = fsub(mb, longTf); // :757-758
+				const int l2 = (int)floorf(i2);
+				t2 = xmulc(pin, xlerp2(gin(l2), gin(l2 + 1), fsub(i2, (float)l2)));
+				x.cE[coef_off(x, s, f, c) + q] = e; // row layout too: the state carry (k_commit, next group's first lane) reads it
+			}
+			tFT[i][j] = ft;
+			tT2[i][j] = t2;
+			tT1[i][j] = t1;
+			tPI[i][j] = pin;
+			tE[i][j] = e;
+		}
+		__syncthreads();
+		for (int r = w; r < 32; r += 8) { // rows of 32 lanes; T1 / PI are consumed L-1 / L steps after the step of their bin
+			const int k = k0 + r;
+			if (k < x.tRows) {
+				x.tFT[t_idx(x, s, grp, k, c, i)] = tFT[r][i];
+				x.tT2[t_idx(x, s, grp, k, c, i)] = tT2[r][i];
+				x.tE[t_idx(x, s, grp, k, c, i)] = tE[r][i];
+			}
+			if (k + LT - 1 < x.tRows) x.tT1[t_idx(x, s, grp, k + LT - 1, c, i)] = tT1[r][i];
+			if (k + LT < x.tRows) x.tPI[t_idx(x, s, grp, k + LT, c, i)] = tPI[r][i];
+		}
+		__syncthreads();
+	}
+}
+
+struct ChainTY { // finals of a chunk of 8 steps, [step][lane] (as ChainTiles::y)
+	float2 y[2][CHAIN_CH][CHAIN_RS2];
+};
+
+template <int CT, int LT>
+__global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
+	const Cfg &g = x.cfg;
+	const int K = g.K;
+	const int lane = threadIdx.x & 31;
+	const int s = x.sBase + blockIdx.x;
+	const Call cl = x.call[s];
+	if (cl.nFrames == 0) return;
+	if (cl.hasRandom && x.randomPathOn) return; // random time factors: k_prep + k_chain take the stream
+	constexpr int D = LT + 1;
+	B200S_SHARED ChainTY T;
+	const int fillI = lane & 7, fillF = lane >> 3;
+
+	for (int base = 0, grp = 0; base < cl.nFrames; base += 32, ++grp) {
+		__syncwarp(); // lane 31's Y of the previous group must be visible to lane 0's loads
+		const int f = base + lane;
+		const bool active = f < cl.nFrames;
+		const Frame fr = x.frames[(size_t)s * x.maxFrames + (active ? f : base)];
+		const bool rotOn = fr.flags & FR_NEW_SPECTRUM;
+		const int nAct = min(32, cl.nFrames - base);
+		const float2 *prevOut[CT];
+		const float *prevE[CT];
+#pragma unroll
+		for (int c = 0; c < CT; ++c) {
+			prevOut[c] = base == 0 ? x.stOut + ((size_t)s * CT + c) * K : x.Y + coef_off(x, s, base - 1, c);
+			prevE[c] = base == 0 ? x.stPredE + ((size_t)s * CT + c) * K : x.cE + coef_off(x, s, base - 1, c);
+		}
+		float2 outHist[CT][LT], pre[CT][LT], t2Fifo[CT][LT], t1Prev[CT], lastFinal[CT];
+		float eFifo[CT][LT], lastE[CT];
+#pragma unroll
+		for (int c = 0; c < CT; ++c) {
+#pragma unroll
+			for (int u = 0; u < LT; ++u) {
+				outHist[c][u] = pre[c][u] = t2Fifo[c][u] = make_float2(0.f, 0.f);
+				eFifo[c][u] = 0.f;
+			}
+			t1Prev[c] = lastFinal[c] = make_float2(0.f, 0.f);
+			lastE[c] = 0.f;
+		}
+		const int steps = K + LT + D * (nAct - 1);
+		// row k of the step-major arrays: this lane's terms of step k (k_products); loaded one step ahead
+		struct Row {
+			float2 ft[CT], t2[CT], t1[CT], pi[CT], p0[CT];
+			float e[CT], p0e[CT];
+		};
+		auto load_row = [&](int k, Row &r) {
+			const int q = k - D * lane;
+#pragma unroll
+			for (int c = 0; c < CT; ++c) {
+				const size_t a = t_idx(x, s, grp, k, c, lane);
+				r.ft[c] = x.tFT[a];
+				r.t2[c] = x.tT2[a];
+				r.t1[c] = x.tT1[a];
+				r.pi[c] = x.tPI[a];
+				r.e[c] = x.tE[a];
+				// lane 0's predecessor block: last call's state or the previous group's rows, at bin q = k
+				const bool p = lane == 0 && q < K;
+				r.p0[c] = p ? prevOut[c][q] : make_float2(0.f, 0.f);
+				r.p0e[c] = p ? prevE[c][q] : 0.f;
+			}
+		};
+		Row cur, nxt;
+		load_row(0, cur);
+		for (int k0 = 0; k0 < steps; k0 += CHAIN_CH) {
+			const int yb = (k0 / CHAIN_CH) & 1;
+#pragma unroll 1
+			for (int i = 0; i < CHAIN_CH; ++i) {
+				const int k = k0 + i;
+				const int q = k - D * lane;
+				const int b = q - LT;
+				if (k + 1 < x.tRows) load_row(k + 1, nxt);
+				// previous block's final output / energy at bin q: finalised by lane-1 last step
+				float2 recvOut[CT];
+				float recvE[CT];
+#pragma unroll
+				for (int c = 0; c < CT; ++c) {
+					recvOut[c].x = __shfl_up_sync(0xffffffffu, lastFinal[c].x, 1);
+					recvOut[c].y = __shfl_up_sync(0xffffffffu, lastFinal[c].y, 1);
+					recvE[c] = __shfl_up_sync(0xffffffffu, lastE[c], 1);
+				}
+				const bool qIn = active && q >= 0 && q < K;
+				if (lane == 0 && qIn) {
+#pragma unroll
+					for (int c = 0; c < CT; ++c) {
+						recvOut[c] = cur.p0[c];
+						recvE[c] = cur.p0e[c];
+					}
+				}
+				// preliminary prediction at bin q (:712-716)
+				float2 newPre[CT], newT2[CT];
+				float newE[CT];
+#pragma unroll
+				for (int c = 0; c < CT; ++c) {
+					newPre[c] = make_float2(0.f, 0.f);
+					newT2[c] = make_float2(0.f, 0.f);
+					newE[c] = 0.f;
+					if (qIn) {
+						const float e = cur.e[c];
+						newT2[c] = cur.t2[c];
+						float2 o = recvOut[c];
+						if (rotOn) o = xmul(o, __ldg(x.rot + q)); // :653
+						const float2 phase = xmul(o, cur.ft[c]);  // :715
+						const float den = fadd(fmaxf(recvE[c], e), B200S_NOISE_FLOOR);
+						newPre[c] = make_float2(fdiv(phase.x, den), fdiv(phase.y, den)); // :716
+						newE[c] = e;
+					}
+				}
+				// advance the FIFOs: afterwards index u <-> bin b+1+u; what falls out belongs to bin b
+				float eAtB[CT];
+				float2 t2AtB[CT];
+#pragma unroll
+				for (int c = 0; c < CT; ++c) {
+					eAtB[c] = eFifo[c][0];
+					t2AtB[c] = t2Fifo[c][0];
+#pragma unroll
+					for (int u = 0; u + 1 < LT; ++u) {
+						pre[c][u] = pre[c][u + 1];
+						eFifo[c][u] = eFifo[c][u + 1];
+						t2Fifo[c][u] = t2Fifo[c][u + 1];
+					}
+					pre[c][LT - 1] = newPre[c];
+					eFifo[c][LT - 1] = newE[c];
+					t2Fifo[c][LT - 1] = newT2[c];
+				}
+				// main prediction at bin b (:727-800)
+				if (active && b >= 0 && b < K) {
+					int m = 0;
+					float maxE = eAtB[0];
+#pragma unroll
+					for (int c = 1; c < CT; ++c) {
+						if (eAtB[c] > maxE) { // :733
+							m = c;
+							maxE = eAtB[c];
+						}
+					}
+					float2 t1Next[CT], pin[CT];
+#pragma unroll
+					for (int c = 0; c < CT; ++c) {
+						t1Next[c] = (b < K - 1) ? cur.t1[c] : make_float2(0.f, 0.f);
+						pin[c] = cur.pi[c];
+					}
+					float2 oh1 = outHist[0][0], ohL = outHist[0][LT - 1], pr1 = pre[0][0], prL = pre[0][LT - 1];
+					float2 t1b = t1Prev[0], t2b = t2AtB[0], t1n = t1Next[0], t2n = t2Fifo[0][LT - 1], pinM = pin[0];
+#pragma unroll
+					for (int c = 1; c < CT; ++c) {
+						if (m == c) {
+							oh1 = outHist[c][0];
+							ohL = outHist[c][LT - 1];
+							pr1 = pre[c][0];
+							prL = pre[c][LT - 1];
+							t1b = t1Prev[c];
+							t2b = t2AtB[c];
+							t1n = t1Next[c];
+							t2n = t2Fifo[c][LT - 1];
+							pinM = pin[c];
+						}
+					}
+					float2 phase = make_float2(0.f, 0.f);
+					if (b > 0) {
+						phase = xadd(phase, xmul(oh1, t1b));              // :754
+						if (b >= LT) phase = xadd(phase, xmul(ohL, t2b)); // :761
+					}
+					if (b < K - 1) {
+						phase = xadd(phase, xmulc(pr1, t1n));                  // :774
+						if (b < K - LT) phase = xadd(phase, xmulc(prL, t2n)); // :784
+					}
+					const float2 outM = make_output(phase, maxE, pinM); // :788
+#pragma unroll
+					for (int c = 0; c < CT; ++c) {
+						float2 oc = outM;
+						if (c != m) { // all other channels are locked in phase (:791-799)
+							const float2 cph = xmul(outM, xmulc(pin[c], pinM));
+							oc = make_output(cph, eAtB[c], pin[c]);
+						}
+#pragma unroll
+						for (int u = LT - 1; u > 0; --u) outHist[c][u] = outHist[c][u - 1];
+						outHist[c][0] = oc;
+						lastFinal[c] = oc;
+						lastE[c] = eAtB[c];
+						t1Prev[c] = t1Next[c];
+						if (c < 2) T.y[c][i][lane] = oc;
+					}
+				}
+				cur = nxt;
+			}
+			__syncwarp();
+			// ---------------- write the chunk's finals back, 64 B per frame ----------------
+#pragma unroll
+			for (int it = 0; it < 8; ++it) {
+				const int fl = fillF + 4 * it, ff = base + fl;
+				if (ff < cl.nFrames) {
+					const int b = k0 + fillI - D * fl - LT;
+					if (b >= 0 && b < K) {
+#pragma unroll
+						for (int c = 0; c < CT; ++c) x.Y[coef_off(x, s, ff, c) + b] = T.y[c][fillI][fl];
+					}
+				}
+			}
+			__syncwarp();
+			(void)yb;
+		}
+	}
+}
+
+} // namespace b200s

@@ -143,6 +143,12 @@ struct Ctx {
 	unsigned long long *diag; // [1] blocks whose random time factors could not be honoured (random path not launched; see engine.cu)
 	int randomOnly;         // k_prep / k_chain launched beside the direct chain kernels: only streams with Call::hasRandom
 	float2 *cT1u, *cT2u;    // [S][F][C][K] the "upwards" twists of a random block (:769-781; the downwards ones are cT1 / cT2)
+	// step-major path of the mapped / formant configurations (chain_t.cuh): map + formant-ratio rows of k_prep's map-only mode,
+	// and the chain's terms transposed by k_products: [S][tGroups][tRows][C][32 lanes]
+	int mapOnly, tRows, tGroups;
+	float *cMapB, *cMapG, *cRatio; // [S][maxFrames][K]
+	float2 *tPI, *tFT, *tT1, *tT2;
+	float *tE;
 	float *cS, *cM; // [S][maxFrames][K]: smoothed energy (:816-848) and formant envelope (:986-1007) of every block: k_energy / k_passes -> k_prep
 	float *cPitch; // [S][maxFrames] freqEstimate of every block when formantBaseFreq <= 0 (k_pitch)
 	// sub-batch of streams this launch covers (the batch is processed as a few sub-batches on

@@ -25,6 +25,7 @@
 #include "chain_direct3.cuh"
 #include "chain_direct4.cuh"
 #include "chain_ws.cuh"
+#include "chain_t.cuh"
 
 using namespace b200s;
 
@@ -82,6 +83,11 @@ struct b200s_engine {
 	int numSMs = 148;
 	float2 *dSpec = 0, *dY = 0, *dPI = 0, *dFT = 0, *dT1 = 0, *dT2 = 0;
 	float *dE = 0, *dS = 0, *dM = 0;
+	// step-major path of the mapped / formant configurations (chain_t.cuh)
+	float *dMapB = 0, *dMapG = 0, *dRatio = 0, *dTE = 0;
+	float2 *dTPI = 0, *dTFT = 0, *dTT1 = 0, *dTT2 = 0;
+	int tFrames = 0;
+	int stepMajor = 1; // b200s_set_tuning key 4: 0 = the round-1 kernels (k_prep + k_chain) for every stream
 	// random time factors beyond 2x stretch (:639-640): engine state per stream (lives as long as the handle, like the
 	// reference's randomEngine member), powers of the multiplier, the upwards twists of random blocks
 	unsigned *dRng = 0, *dRngPow = 0;
@@ -142,7 +148,8 @@ static void free_all(b200s_engine *e) {
 	dfree(e->dSched); dfree(e->dHist[0]); dfree(e->dHist[1]); dfree(e->dPend); dfree(e->dPendWp);
 	dfree(e->dStIn); dfree(e->dStPrev); dfree(e->dStOut); dfree(e->dStPredE); dfree(e->dStIl);
 	dfree(e->dFrames); dfree(e->dCall); dfree(e->dJobs); dfree(e->dSpec); dfree(e->dY); dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dE); dfree(e->dS); dfree(e->dM); dfree(e->dT1u); dfree(e->dT2u); dfree(e->dRngPow); dfree(e->dStPitch);
-	e->randFrames = 0; dfree(e->dPitch);
+	dfree(e->dMapB); dfree(e->dMapG); dfree(e->dRatio); dfree(e->dTE); dfree(e->dTPI); dfree(e->dTFT); dfree(e->dTT1); dfree(e->dTT2);
+	e->randFrames = e->tFrames = 0; dfree(e->dPitch);
 	dfree(e->dIn); dfree(e->dOut); dfree(e->dZero); dfree(e->dTmp); dfree(e->dIn16); dfree(e->dOut16);
 	e->in16Cap = e->out16Cap = 0;
 	e->maxFrames = e->coefFrames = 0;
@@ -168,6 +175,8 @@ static Ctx make_ctx(b200s_engine *e) {
 	x.sBase = 0; x.sCount = e->S;
 	x.frames = e->dFrames; x.call = e->dCall; x.jobs = e->dJobs;
 	x.spec = e->dSpec; x.Y = e->dY; x.cPI = e->dPI; x.cFT = e->dFT; x.cT1 = e->dT1; x.cT2 = e->dT2; x.cE = e->dE; x.cS = e->dS; x.cM = e->dM; x.cT1u = e->dT1u; x.cT2u = e->dT2u;
+	x.cMapB = e->dMapB; x.cMapG = e->dMapG; x.cRatio = e->dRatio; x.tE = e->dTE; x.tPI = e->dTPI; x.tFT = e->dTFT; x.tT1 = e->dTT1; x.tT2 = e->dTT2;
+	x.tRows = t_rows(e->cfg); x.tGroups = (e->maxFrames + 31) / 32;
 	x.rngState = e->dRng; x.rngPow = e->dRngPow; x.rngJump = e->rngJump; x.diag = e->dDiag; x.stPitch = e->dStPitch; x.cPitch = e->dPitch;
 	return x;
 }
@@ -310,6 +319,20 @@ static ChainKernel chain3_kernel(const Cfg &g, int v, bool fast) {
 	default: return k_chain_direct3<8>;
 	}
 }
+template <int CT>
+static ChainKernel chain_t_kernel_for(int L) {
+	switch (L) {
+	case 1: return k_chain_t<CT, 1>;
+	case 2: return k_chain_t<CT, 2>;
+	case 3: return k_chain_t<CT, 3>;
+	case 4: return k_chain_t<CT, 4>;
+	case 5: return k_chain_t<CT, 5>;
+	case 6: return k_chain_t<CT, 6>;
+	case 7: return k_chain_t<CT, 7>;
+	default: return k_chain_t<CT, 8>;
+	}
+}
+static ChainKernel chain_t_kernel(const Cfg &g) { return g.C == 1 ? chain_t_kernel_for<1>(g.L) : chain_t_kernel_for<2>(g.L); }
 static ChainKernel chain_kernel(const Cfg &g, bool direct) {
 	return g.C == 1 ? chain_kernel_for<1>(g.L, direct) : chain_kernel_for<2>(g.L, direct);
 }
@@ -551,7 +574,8 @@ static int ensure_scratch(b200s_engine *e, int nOut) {
 	e->maxFrames = need;
 	// the complex coefficient rows follow maxFrames (their row offsets use it) but only exist once a call needed them
 	dfree(e->dPI); dfree(e->dFT); dfree(e->dT1); dfree(e->dT2); dfree(e->dS); dfree(e->dM); dfree(e->dT1u); dfree(e->dT2u);
-	e->coefFrames = e->randFrames = 0;
+	dfree(e->dMapB); dfree(e->dMapG); dfree(e->dRatio); dfree(e->dTE); dfree(e->dTPI); dfree(e->dTFT); dfree(e->dTT1); dfree(e->dTT2);
+	e->coefFrames = e->randFrames = e->tFrames = 0;
 	return 0;
 }
 // Complex coefficient rows of k_prep (32 B per bin-channel and block: 6.6 GB at batch 1024 x 33 blocks stereo): only calls
@@ -573,6 +597,27 @@ static int ensure_coef(b200s_engine *e) {
 	if ((rc = dalloc(e, &e->dS, n / g.C))) return rc; // smoothed energy / formant envelope rows: one per block (k_passes)
 	if ((rc = dalloc(e, &e->dM, n / g.C))) return rc;
 	e->coefFrames = e->maxFrames;
+	return 0;
+}
+// rows of the step-major path (mapped / formant calls): map, ratio, smoothed energy, envelope, and the transposed terms
+static int ensure_stepmajor(b200s_engine *e) {
+	if (e->tFrames == e->maxFrames && e->dTFT) return 0;
+	const Cfg &g = e->cfg;
+	CK(cudaStreamSynchronize(e->stream));
+	const size_t nRow = (size_t)g.S * e->maxFrames * g.K;
+	const size_t nT = (size_t)g.S * ((e->maxFrames + 31) / 32) * t_rows(g) * g.C * 32;
+	int rc;
+	if ((rc = dalloc(e, &e->dMapB, nRow))) return rc;
+	if ((rc = dalloc(e, &e->dMapG, nRow))) return rc;
+	if ((rc = dalloc(e, &e->dRatio, nRow))) return rc;
+	if (!e->dS && (rc = dalloc(e, &e->dS, nRow))) return rc;
+	if (!e->dM && (rc = dalloc(e, &e->dM, nRow))) return rc;
+	if ((rc = dalloc(e, &e->dTE, nT))) return rc;
+	if ((rc = dalloc(e, &e->dTPI, nT))) return rc;
+	if ((rc = dalloc(e, &e->dTFT, nT))) return rc;
+	if ((rc = dalloc(e, &e->dTT1, nT))) return rc;
+	if ((rc = dalloc(e, &e->dTT2, nT))) return rc;
+	e->tFrames = e->maxFrames;
 	return 0;
 }
 // the two extra twist rows of blocks with random time factors (calls that may stretch beyond 2x only)
@@ -621,11 +666,13 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 		e->prevCallMayRandom = lowRatio;
 		e->seekMayRandom = false;
 	}
-	if ((!params_plain(e) || mayRandom) && (rc = ensure_coef(e))) return rc;
+	const bool useStepMajor = !params_plain(e) && e->stepMajor; // mapped / formant call on k_products + k_chain_t
+	if (((!params_plain(e) && !useStepMajor) || mayRandom) && (rc = ensure_coef(e))) return rc;
+	if (useStepMajor && (rc = ensure_stepmajor(e))) return rc;
 	if (mayRandom && (rc = ensure_rand(e))) return rc;
 	Ctx x = make_ctx(e);
 	if (!mayRandom) x.cT1u = x.cT2u = nullptr; // (stale rows of an earlier call are never read)
-	x.randomPathOn = (mayRandom || !params_plain(e)) ? 1 : 0; // mapped / formant calls run k_prep + k_chain for every stream anyway
+	x.randomPathOn = (mayRandom || (!params_plain(e) && !useStepMajor)) ? 1 : 0; // the round-1 mapped path runs k_prep + k_chain for every stream anyway
 	x.in = dIn; x.out = dOut; x.nIn = nIn; x.nOut = nOut;
 	x.inChanStride = inChanStride; x.inStreamStride = inStreamStride;
 	x.outChanStride = outChanStride; x.outStreamStride = outStreamStride;
@@ -697,11 +744,41 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 					CKL();
 					B200S_LAUNCH(k_passes, dim3(x.sCount), dim3(32), 0, st, x);
 					CKL();
-					B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g, formantsOn), st, x);
-					CKL();
+					if (useStepMajor) { // peaks / map / ratio rows, then the per-bin terms in step-major order (chain_t.cuh)
+						x.mapOnly = 1;
+						B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g, formantsOn), st, x);
+						CKL();
+						x.mapOnly = 0;
+						B200S_LAUNCH(k_products, dim3(x.tRows / 32, x.tGroups, x.sCount), dim3(256), 0, st, x);
+						CKL();
+						if (mayRandom) { // streams with a random block: the full k_prep (random-only mode), consumed by k_chain below
+							x.randomOnly = 1;
+							B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g, formantsOn), st, x);
+							CKL();
+							x.randomOnly = 0;
+						}
+					} else {
+						B200S_LAUNCH(k_prep, dim3(F, x.sCount), dim3(kThreads), smem_prep(g, formantsOn), st, x);
+						CKL();
+					}
 					if ((_rc = prof_mark(e, PK_PREP, false))) return _rc;
 				}
-				if (plain && chainV == 5) {
+				if (useStepMajor) {
+					int _rc;
+					if ((_rc = prof_mark(e, PK_CHAIN, true))) return _rc;
+					ChainKernel kt = chain_t_kernel(g);
+					B200S_LAUNCH(kt, dim3(x.sCount), dim3(32), 0, st, x);
+					CKL();
+					if (mayRandom) { // the streams k_chain_t left (Call::hasRandom)
+						x.randomOnly = 1;
+						dim3 grid((x.sCount + kChainWarps - 1) / kChainWarps), block(32 * kChainWarps);
+						ChainKernel kc = chain_kernel(g, false);
+						B200S_LAUNCH(kc, grid, block, smem_chain(g, false, true), st, x);
+						CKL();
+						x.randomOnly = 0;
+					}
+					if ((_rc = prof_mark(e, PK_CHAIN, false))) return _rc;
+				} else if (plain && chainV == 5) {
 					int _rc;
 					if ((_rc = prof_mark(e, PK_CHAIN, true))) return _rc;
 					const bool fast = !e->exactMath;
@@ -976,6 +1053,7 @@ int b200s_set_tuning(b200s_engine *e, int key, int value) {
 	else if (key == 1 && (value == 0 || value == 1)) e->fftV1 = value;
 	else if (key == 2 && value >= 1) e->nHostParts = std::min(value, (int)b200s_engine::kMaxSub);
 	else if (key == 3 && (value == 0 || value == 1)) e->exactMath = value;
+	else if (key == 4 && (value == 0 || value == 1)) e->stepMajor = value;
 	else {
 		e->err = "b200s_set_tuning: unknown key or value";
 		return B200S_EINVAL;
@@ -1003,7 +1081,7 @@ int b200s_reserve(b200s_engine *e, int maxIn, int maxOut) {
 	NEED_CFG();
 	int rc;
 	if ((rc = ensure_scratch(e, maxOut))) return rc;
-	if (!params_plain(e) && (rc = ensure_coef(e))) return rc;
+	if (!params_plain(e) && (rc = e->stepMajor ? ensure_stepmajor(e) : ensure_coef(e))) return rc;
 	if ((rc = stage_in(e, 0, 0))) return rc;
 	size_t ci = (size_t)e->cfg.S * e->cfg.C * std::max(maxIn, 1), co = (size_t)e->cfg.S * e->cfg.C * std::max(maxOut, 1);
 	if ((rc = ensure_buf(e, &e->dIn, &e->inCap, ci, false))) return rc;
