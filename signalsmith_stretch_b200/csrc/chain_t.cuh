@@ -44,28 +44,39 @@ __global__ void __launch_bounds__(256) k_products(Ctx x) {
 			float2 ft = make_float2(0.f, 0.f), t1 = ft, t2 = ft, pin = ft;
 			float e = 0.f;
 			const int q = k0 + i - D * j;
+			// everything that depends on the block only: once per warp iteration (the lanes of a warp share j)
+			const int f = base + min(j, nAct - 1);
+			const Frame fr = x.frames[(size_t)s * x.maxFrames + f];
+			const bool mapped = fr.flags & FR_MAPPED, formants = fr.flags & FR_FORMANTS, rotOn = fr.flags & FR_NEW_SPECTRUM;
+			const float2 *inRow = spec_slot(x, s, fr.inSlot, c), *pvRow = spec_slot(x, s, fr.prevSlot, c); // (mapped calls: planar spectra)
+			const size_t row = ((size_t)s * x.maxFrames + f) * K;
+			const float *mapB = x.cMapB + row, *mapG = x.cMapG + row, *ratio = x.cRatio + row;
+			float *eRow = x.cE + coef_off(x, s, f, c);
+			const float tf = fmaxf(fr.timeFactor, 1.0f / B200S_MAX_CLEAN_STRETCH); // :638
+			const float longTf = fmul((float)LT, tf);
 			if (j < nAct && q >= 0 && q < K) {
-				const int f = base + j;
-				const Frame fr = x.frames[(size_t)s * x.maxFrames + f];
-				const bool mapped = fr.flags & FR_MAPPED, formants = fr.flags & FR_FORMANTS, rotOn = fr.flags & FR_NEW_SPECTRUM;
-				const size_t row = ((size_t)s * x.maxFrames + f) * K;
-				const float tf = fmaxf(fr.timeFactor, 1.0f / B200S_MAX_CLEAN_STRETCH); // :638
-				const float longTf = fmul((float)LT, tf);
-				auto gin = [&](int b) { return (b < 0 || b >= K) ? make_float2(0.f, 0.f) : spec_val(x, s, fr.inSlot, c, b); };
-				auto gpv = [&](int b) { // prevInput is rotated in place before being interpolated (:654)
-					if (b < 0 || b >= K) return make_float2(0.f, 0.f);
-					const float2 v = spec_val(x, s, fr.prevSlot, c, b);
-					return rotOn ? xmul(v, __ldg(x.rot + b)) : v;
+				// gathers without branches: clamped address, value selected afterwards (zero outside the spectrum, :564-568)
+				auto gin = [&](int b) {
+					const float2 v = inRow[min(max(b, 0), K - 1)];
+					const bool in = (unsigned)b < (unsigned)K;
+					return make_float2(in ? v.x : 0.f, in ? v.y : 0.f);
 				};
-				const float mb = mapped ? x.cMapB[row + q] : (float)q;
-				const float mg = mapped ? x.cMapG[row + q] : 1.f;
+				auto gpv = [&](int b) { // prevInput is rotated in place before being interpolated (:654)
+					const int bc = min(max(b, 0), K - 1);
+					const float2 v = pvRow[bc], vr = xmul(v, __ldg(x.rot + bc));
+					const bool in = (unsigned)b < (unsigned)K;
+					return make_float2(in ? (rotOn ? vr.x : v.x) : 0.f, in ? (rotOn ? vr.y : v.y) : 0.f);
+				};
+				const float mb = mapped ? mapB[q] : (float)q;
+				const float mg = mapped ? mapG[q] : 1.f;
 				const int lo = (int)floorf(mb);
 				const float frac = fsub(mb, (float)lo);
 				const float2 inLo = gin(lo), inHi = gin(lo + 1);
 				float eLo = xnorm(inLo), eHi = xnorm(inHi); // Band::inputEnergy (:679,:826)
 				if (formants) {
-					if (lo >= 0 && lo < K) eLo = fmul(eLo, x.cRatio[row + lo]);
-					if (lo + 1 >= 0 && lo + 1 < K) eHi = fmul(eHi, x.cRatio[row + lo + 1]);
+					const float rLo = ratio[min(max(lo, 0), K - 1)], rHi = ratio[min(max(lo + 1, 0), K - 1)];
+					eLo = (unsigned)lo < (unsigned)K ? fmul(eLo, rLo) : eLo;
+					eHi = (unsigned)(lo + 1) < (unsigned)K ? fmul(eHi, rHi) : eHi;
 				}
 				e = fmul(xlerp(eLo, eHi, frac), fmaxf(0.f, mg)); // :708-709
 				pin = xlerp2(inLo, inHi, frac);                  // :710
@@ -77,7 +88,7 @@ __global__ void __launch_bounds__(256) k_products(Ctx x) {
 				const float i2 = fsub(mb, longTf); // :757-758
 				const int l2 = (int)floorf(i2);
 				t2 = xmulc(pin, xlerp2(gin(l2), gin(l2 + 1), fsub(i2, (float)l2)));
-				x.cE[coef_off(x, s, f, c) + q] = e; // row layout too: the state carry (k_commit, next group's first lane) reads it
+				eRow[q] = e; // row layout too: the state carry (k_commit, next group's first lane) reads it
 			}
 			tFT[i][j] = ft;
 			tT2[i][j] = t2;
@@ -86,15 +97,17 @@ __global__ void __launch_bounds__(256) k_products(Ctx x) {
 			tE[i][j] = e;
 		}
 		__syncthreads();
+		const size_t a0 = t_idx(x, s, grp, k0, c, i), st = (size_t)g.C * 32; // element of row k0; elements per row
 		for (int r = w; r < 32; r += 8) { // rows of 32 lanes; T1 / PI are consumed L-1 / L steps after the step of their bin
 			const int k = k0 + r;
+			const size_t a = a0 + (size_t)r * st;
 			if (k < x.tRows) {
-				x.tFT[t_idx(x, s, grp, k, c, i)] = tFT[r][i];
-				x.tT2[t_idx(x, s, grp, k, c, i)] = tT2[r][i];
-				x.tE[t_idx(x, s, grp, k, c, i)] = tE[r][i];
+				x.tFT[a] = tFT[r][i];
+				x.tT2[a] = tT2[r][i];
+				x.tE[a] = tE[r][i];
 			}
-			if (k + LT - 1 < x.tRows) x.tT1[t_idx(x, s, grp, k + LT - 1, c, i)] = tT1[r][i];
-			if (k + LT < x.tRows) x.tPI[t_idx(x, s, grp, k + LT, c, i)] = tPI[r][i];
+			if (k + LT - 1 < x.tRows) x.tT1[a + (size_t)(LT - 1) * st] = tT1[r][i];
+			if (k + LT < x.tRows) x.tPI[a + (size_t)LT * st] = tPI[r][i];
 		}
 		__syncthreads();
 	}
@@ -149,24 +162,28 @@ __global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
 			float2 ft[CT], t2[CT], t1[CT], pi[CT], p0[CT];
 			float e[CT], p0e[CT];
 		};
+		const size_t a00 = t_idx(x, s, grp, 0, 0, lane);
+		const float2 *pFT = x.tFT + a00, *pT2 = x.tT2 + a00, *pT1 = x.tT1 + a00, *pPI = x.tPI + a00;
+		const float *pE = x.tE + a00;
 		auto load_row = [&](int k, Row &r) {
 			const int q = k - D * lane;
 #pragma unroll
 			for (int c = 0; c < CT; ++c) {
-				const size_t a = t_idx(x, s, grp, k, c, lane);
-				r.ft[c] = x.tFT[a];
-				r.t2[c] = x.tT2[a];
-				r.t1[c] = x.tT1[a];
-				r.pi[c] = x.tPI[a];
-				r.e[c] = x.tE[a];
+				const size_t a = ((size_t)k * CT + c) * 32;
+				r.ft[c] = pFT[a];
+				r.t2[c] = pT2[a];
+				r.t1[c] = pT1[a];
+				r.pi[c] = pPI[a];
+				r.e[c] = pE[a];
 				// lane 0's predecessor block: last call's state or the previous group's rows, at bin q = k
 				const bool p = lane == 0 && q < K;
 				r.p0[c] = p ? prevOut[c][q] : make_float2(0.f, 0.f);
 				r.p0e[c] = p ? prevE[c][q] : 0.f;
 			}
 		};
-		Row cur, nxt;
+		Row cur, nxt, nx2; // the rows of this step and of the next two (two steps of latency hiding for the L2 / HBM loads)
 		load_row(0, cur);
+		load_row(1, nxt);
 		for (int k0 = 0; k0 < steps; k0 += CHAIN_CH) {
 			const int yb = (k0 / CHAIN_CH) & 1;
 #pragma unroll 1
@@ -174,7 +191,7 @@ __global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
 				const int k = k0 + i;
 				const int q = k - D * lane;
 				const int b = q - LT;
-				if (k + 1 < x.tRows) load_row(k + 1, nxt);
+				if (k + 2 < x.tRows) load_row(k + 2, nx2);
 				// previous block's final output / energy at bin q: finalised by lane-1 last step
 				float2 recvOut[CT];
 				float recvE[CT];
@@ -207,7 +224,7 @@ __global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
 						if (rotOn) o = xmul(o, __ldg(x.rot + q)); // :653
 						const float2 phase = xmul(o, cur.ft[c]);  // :715
 						const float den = fadd(fmaxf(recvE[c], e), B200S_NOISE_FLOOR);
-						newPre[c] = make_float2(fdiv(phase.x, den), fdiv(phase.y, den)); // :716
+						newPre[c] = make_float2(fdivq(phase.x, den), fdivq(phase.y, den)); // :716 (branch-free, correctly rounded: kernels.cuh)
 						newE[c] = e;
 					}
 				}
@@ -270,13 +287,13 @@ __global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
 						phase = xadd(phase, xmulc(pr1, t1n));                  // :774
 						if (b < K - LT) phase = xadd(phase, xmulc(prL, t2n)); // :784
 					}
-					const float2 outM = make_output(phase, maxE, pinM); // :788
+					const float2 outM = make_output_q(phase, maxE, pinM); // :788
 #pragma unroll
 					for (int c = 0; c < CT; ++c) {
 						float2 oc = outM;
 						if (c != m) { // all other channels are locked in phase (:791-799)
 							const float2 cph = xmul(outM, xmulc(pin[c], pinM));
-							oc = make_output(cph, eAtB[c], pin[c]);
+							oc = make_output_q(cph, eAtB[c], pin[c]);
 						}
 #pragma unroll
 						for (int u = LT - 1; u > 0; --u) outHist[c][u] = outHist[c][u - 1];
@@ -288,6 +305,7 @@ __global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
 					}
 				}
 				cur = nxt;
+				nxt = nx2;
 			}
 			__syncwarp();
 			// ---------------- write the chunk's finals back, 64 B per frame ----------------
