@@ -161,12 +161,14 @@ __global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
 		struct Row {
 			float2 ft[CT], t2[CT], t1[CT], pi[CT], p0[CT];
 			float e[CT], p0e[CT];
+			float2 rot; // rot[q] of the step (:647-655 table), fetched with the row so that nothing waits for it
 		};
 		const size_t a00 = t_idx(x, s, grp, 0, 0, lane);
 		const float2 *pFT = x.tFT + a00, *pT2 = x.tT2 + a00, *pT1 = x.tT1 + a00, *pPI = x.tPI + a00;
 		const float *pE = x.tE + a00;
 		auto load_row = [&](int k, Row &r) {
 			const int q = k - D * lane;
+			r.rot = __ldg(x.rot + min(max(q, 0), K - 1));
 #pragma unroll
 			for (int c = 0; c < CT; ++c) {
 				const size_t a = ((size_t)k * CT + c) * 32;
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
 						const float e = cur.e[c];
 						newT2[c] = cur.t2[c];
 						float2 o = recvOut[c];
-						if (rotOn) o = xmul(o, __ldg(x.rot + q)); // :653
+						if (rotOn) o = xmul(o, cur.rot); // :653
 						const float2 phase = xmul(o, cur.ft[c]);  // :715
 						const float den = fadd(fmaxf(recvE[c], e), B200S_NOISE_FLOOR);
 						newPre[c] = make_float2(fdivq(phase.x, den), fdivq(phase.y, den)); // :716 (branch-free, correctly rounded: kernels.cuh)
