@@ -237,8 +237,20 @@ class BatchStretch:
             raise StretchError("engine not configured: call presetDefault / presetCheaper / configure first")
         return (self.batch, c, n)
 
+    def _adopt_torch_stream(self):
+        """Device-pointer calls are enqueued on torch's CURRENT stream (b200s_set_stream), so they are ordered after the
+        producers of `inputs` and before any torch op on the returned tensor, like a torch op.  (The engine's own side
+        streams fork from and join that stream.)"""
+        import torch
+
+        st = torch.cuda.current_stream().cuda_stream
+        if getattr(self, "_torch_stream", None) != st:
+            self._ck(self._lib.b200s_set_stream(self._h, ctypes.c_void_p(st)))
+            self._torch_stream = st
+
     def seek(self, inputs, playbackRate):
         if _is_torch_cuda(inputs):
+            self._adopt_torch_stream()
             n = inputs.shape[-1]
             self._ck(self._lib.b200s_seek_device(self._h, inputs.data_ptr(), n, float(playbackRate)))
             return
@@ -273,6 +285,7 @@ class BatchStretch:
         if _is_torch_cuda(inputs):
             import torch
 
+            self._adopt_torch_stream()
             n_in = inputs.shape[-1]
             assert inputs.is_contiguous() and inputs.dtype == torch.float32
             if out is None:

@@ -113,8 +113,10 @@ __global__ void __launch_bounds__(256) k_products(Ctx x) {
 	}
 }
 
-struct ChainTY { // finals of a chunk of 8 steps, [step][lane] (as ChainTiles::y)
-	float2 y[2][CHAIN_CH][CHAIN_RS2];
+#define CT_CH 12 // steps per chunk: rows rotate through 3 register sets and the FIFOs through L slots, so 12 steps (L in
+                 // {1,2,3,4,6}) bring every rotation back to its start and the steps are unrolled with compile-time renaming only
+struct ChainTY { // finals of a chunk, [step][lane]
+	float2 y[2][CT_CH][CHAIN_RS2];
 };
 
 template <int CT, int LT>
@@ -127,8 +129,8 @@ __global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
 	if (cl.nFrames == 0) return;
 	if (cl.hasRandom && x.randomPathOn) return; // random time factors: k_prep + k_chain take the stream
 	constexpr int D = LT + 1;
+	constexpr bool ROT = (CT_CH % LT) == 0; // FIFO slots by compile-time rotation; otherwise (L = 5, 7, 8) they are shifted
 	B200S_SHARED ChainTY T;
-	const int fillI = lane & 7, fillF = lane >> 3;
 
 	for (int base = 0, grp = 0; base < cl.nFrames; base += 32, ++grp) {
 		__syncwarp(); // lane 31's Y of the previous group must be visible to lane 0's loads
@@ -144,6 +146,8 @@ __global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
 			prevOut[c] = base == 0 ? x.stOut + ((size_t)s * CT + c) * K : x.Y + coef_off(x, s, base - 1, c);
 			prevE[c] = base == 0 ? x.stPredE + ((size_t)s * CT + c) * K : x.cE + coef_off(x, s, base - 1, c);
 		}
+		// per-lane register FIFOs.  Rotating form (ROT), at step t: slot t % L holds the values of bin b (pushed L steps ago) and
+		// takes those of bin q = b + L; the final of bin b - 1 - u sits in slot (t - 1 - u) % L.  Shifted form: as k_chain.
 		float2 outHist[CT][LT], pre[CT][LT], t2Fifo[CT][LT], t1Prev[CT], lastFinal[CT];
 		float eFifo[CT][LT], lastE[CT];
 #pragma unroll
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
 			lastE[c] = 0.f;
 		}
 		const int steps = K + LT + D * (nAct - 1);
-		// row k of the step-major arrays: this lane's terms of step k (k_products); loaded one step ahead
+		// row k of the step-major arrays: this lane's terms of step k (k_products), fetched two steps ahead
 		struct Row {
 			float2 ft[CT], t2[CT], t1[CT], pi[CT], p0[CT];
 			float e[CT], p0e[CT];
@@ -183,17 +187,17 @@ __global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
 				r.p0e[c] = p ? prevE[c][q] : 0.f;
 			}
 		};
-		Row cur, nxt, nx2; // the rows of this step and of the next two (two steps of latency hiding for the L2 / HBM loads)
-		load_row(0, cur);
-		load_row(1, nxt);
-		for (int k0 = 0; k0 < steps; k0 += CHAIN_CH) {
-			const int yb = (k0 / CHAIN_CH) & 1;
-#pragma unroll 1
-			for (int i = 0; i < CHAIN_CH; ++i) {
-				const int k = k0 + i;
+		Row rows[3]; // rows[t % 3]: the row of step t; the one of step t + 2 is loaded while step t is computed
+		load_row(0, rows[0]);
+		load_row(1, rows[1]);
+		for (int k0 = 0; k0 < steps; k0 += CT_CH) {
+			static_for<CT_CH>([&](auto tc) {
+				constexpr int t = decltype(tc)::value;
+				const Row &cur = rows[t % 3];
+				const int k = k0 + t;
 				const int q = k - D * lane;
 				const int b = q - LT;
-				if (k + 2 < x.tRows) load_row(k + 2, nx2);
+				if (k + 2 < x.tRows) load_row(k + 2, rows[(t + 2) % 3]);
 				// previous block's final output / energy at bin q: finalised by lane-1 last step
 				float2 recvOut[CT];
 				float recvE[CT];
@@ -230,22 +234,29 @@ __global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
 						newE[c] = e;
 					}
 				}
-				// advance the FIFOs: afterwards index u <-> bin b+1+u; what falls out belongs to bin b
+				// what belongs to bin b leaves the FIFOs, the values of bin q enter
+				constexpr int S0 = ROT ? t % LT : 0;                    // slot of bin b (and, afterwards, of bin q)
+				constexpr int S1 = ROT ? (t + 1) % LT : 0;              // bin b + 1 (after the push)
+				constexpr int SQ = ROT ? t % LT : LT - 1;               // bin q (after the push)
+				constexpr int H1 = ROT ? (t + LT - 1) % LT : 0;         // final of bin b - 1
+				constexpr int HL = ROT ? t % LT : LT - 1;               // final of bin b - L
 				float eAtB[CT];
 				float2 t2AtB[CT];
 #pragma unroll
 				for (int c = 0; c < CT; ++c) {
-					eAtB[c] = eFifo[c][0];
-					t2AtB[c] = t2Fifo[c][0];
+					eAtB[c] = eFifo[c][S0];
+					t2AtB[c] = t2Fifo[c][S0];
+					if constexpr (!ROT) {
 #pragma unroll
-					for (int u = 0; u + 1 < LT; ++u) {
-						pre[c][u] = pre[c][u + 1];
-						eFifo[c][u] = eFifo[c][u + 1];
-						t2Fifo[c][u] = t2Fifo[c][u + 1];
+						for (int u = 0; u + 1 < LT; ++u) {
+							pre[c][u] = pre[c][u + 1];
+							eFifo[c][u] = eFifo[c][u + 1];
+							t2Fifo[c][u] = t2Fifo[c][u + 1];
+						}
 					}
-					pre[c][LT - 1] = newPre[c];
-					eFifo[c][LT - 1] = newE[c];
-					t2Fifo[c][LT - 1] = newT2[c];
+					pre[c][SQ] = newPre[c];
+					eFifo[c][SQ] = newE[c];
+					t2Fifo[c][SQ] = newT2[c];
 				}
 				// main prediction at bin b (:727-800)
 				if (active && b >= 0 && b < K) {
@@ -264,19 +275,20 @@ __global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
 						t1Next[c] = (b < K - 1) ? cur.t1[c] : make_float2(0.f, 0.f);
 						pin[c] = cur.pi[c];
 					}
-					float2 oh1 = outHist[0][0], ohL = outHist[0][LT - 1], pr1 = pre[0][0], prL = pre[0][LT - 1];
-					float2 t1b = t1Prev[0], t2b = t2AtB[0], t1n = t1Next[0], t2n = t2Fifo[0][LT - 1], pinM = pin[0];
+					// (L = 1: bin b + 1 IS bin q, i.e. slot SQ)
+					float2 oh1 = outHist[0][H1], ohL = outHist[0][HL], pr1 = pre[0][LT == 1 ? SQ : S1], prL = pre[0][SQ];
+					float2 t1b = t1Prev[0], t2b = t2AtB[0], t1n = t1Next[0], t2n = t2Fifo[0][SQ], pinM = pin[0];
 #pragma unroll
 					for (int c = 1; c < CT; ++c) {
 						if (m == c) {
-							oh1 = outHist[c][0];
-							ohL = outHist[c][LT - 1];
-							pr1 = pre[c][0];
-							prL = pre[c][LT - 1];
+							oh1 = outHist[c][H1];
+							ohL = outHist[c][HL];
+							pr1 = pre[c][LT == 1 ? SQ : S1];
+							prL = pre[c][SQ];
 							t1b = t1Prev[c];
 							t2b = t2AtB[c];
 							t1n = t1Next[c];
-							t2n = t2Fifo[c][LT - 1];
+							t2n = t2Fifo[c][SQ];
 							pinM = pin[c];
 						}
 					}
@@ -297,33 +309,33 @@ __global__ void __launch_bounds__(32) k_chain_t(Ctx x) {
 							const float2 cph = xmul(outM, xmulc(pin[c], pinM));
 							oc = make_output_q(cph, eAtB[c], pin[c]);
 						}
+						if constexpr (!ROT) {
 #pragma unroll
-						for (int u = LT - 1; u > 0; --u) outHist[c][u] = outHist[c][u - 1];
-						outHist[c][0] = oc;
+							for (int u = LT - 1; u > 0; --u) outHist[c][u] = outHist[c][u - 1];
+						}
+						outHist[c][ROT ? t % LT : 0] = oc; // (rotating: replaces the final of bin b - L, read above)
 						lastFinal[c] = oc;
 						lastE[c] = eAtB[c];
 						t1Prev[c] = t1Next[c];
-						if (c < 2) T.y[c][i][lane] = oc;
+						T.y[c][t][lane] = oc;
 					}
 				}
-				cur = nxt;
-				nxt = nx2;
-			}
+			});
 			__syncwarp();
-			// ---------------- write the chunk's finals back, 64 B per frame ----------------
+			// ---------------- write the chunk's finals back: 32 B (4 bins) per frame and quarter-warp ----------------
 #pragma unroll
-			for (int it = 0; it < 8; ++it) {
-				const int fl = fillF + 4 * it, ff = base + fl;
-				if (ff < cl.nFrames) {
-					const int b = k0 + fillI - D * fl - LT;
-					if (b >= 0 && b < K) {
+			for (int m4 = 0; m4 < CT_CH / 4; ++m4) {
 #pragma unroll
-						for (int c = 0; c < CT; ++c) x.Y[coef_off(x, s, ff, c) + b] = T.y[c][fillI][fl];
+				for (int it = 0; it < 4; ++it) {
+					const int t = 4 * m4 + (lane & 3), fl = (lane >> 2) + 8 * it, ff = base + fl;
+					const int b = k0 + t - D * fl - LT;
+					if (ff < cl.nFrames && b >= 0 && b < K) {
+#pragma unroll
+						for (int c = 0; c < CT; ++c) x.Y[coef_off(x, s, ff, c) + b] = T.y[c][t][fl];
 					}
 				}
 			}
 			__syncwarp();
-			(void)yb;
 		}
 	}
 }

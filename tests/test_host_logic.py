@@ -90,6 +90,10 @@ SMALL = [
     # setFormantBase(0): automatic pitch estimate per block (estimateFrequency :929-966, k_pitch), state carried over calls
     ("formant_auto_pitch_stereo", lambda o: (o.configure(2, 512, 128), o.setTransposeSemitones(5, 0), o.setFormantFactor(1, True), o.setFormantBase(0)), 2, 1.0, 640),
     ("formant_auto_pitch_+4st_0.8x", lambda o: (o.configure(1, 384, 96), o.setFormantSemitones(4, False), o.setFormantBase(0)), 1, 0.8, 500),
+    # long vertical steps that do not divide the 12-step unrolling of k_chain_t (its FIFOs are then shifted, not rotated)
+    ("L5_mapped_stereo", lambda o: (o.configure(2, 500, 100), o.setTransposeSemitones(4, 0.2)), 2, 1.0, 700),
+    ("L8_mapped_mono_1.25x", lambda o: (o.configure(1, 512, 64), o.setTransposeSemitones(-3, 0)), 1, 1.25, 640),
+    ("L2_mapped_formants", lambda o: (o.configure(1, 512, 256), o.setTransposeSemitones(5, 0), o.setFormantFactor(1, True), o.setFormantBase(150 / 48000)), 1, 1.0, 1024),
 ]
 
 
