@@ -130,32 +130,43 @@ class LiveBatch:
         self._ls[s], self._le[s], self._active[s] = seg["loopStart"], seg["loopEnd"], seg["active"]
         self._next[s] = tm[1]["output"] if len(tm) > 1 else np.inf
 
-    def schedule(self, s, obj_in, adjust_previous=False):  # :67-108
+    def schedule(self, s, obj_in, adjust_previous=False):
+        """Insert a time-map point for stream `s` (semantics of the worklet's `schedule`, web-wrapper.js:67-108).
+        `obj_in`: any of outputTime (default: now), input, rate, active, loopStart, loopEnd.  Points at or after the new
+        one are discarded; fields that are not given are inherited from the earliest discarded point (else from the last
+        point of the map); a missing `input` is that point's playback extrapolated to the new time (or stands still if it
+        was stopped).  adjust_previous: re-aim the preceding
+        segment so that it arrives exactly at the new point (its start is first moved up to "now" if already passed)."""
         self._to_map(s)
-        tm = self.time_maps[s]
-        output_time = obj_in.get("outputTime", self.current_time)
-        latest = tm[-1]
-        while tm and tm[-1]["output"] >= output_time:
-            latest = tm.pop()
-        obj = dict(latest)
-        obj.update(input=None, output=output_time)
-        obj.update({k: v for k, v in obj_in.items() if k != "outputTime"})
-        if obj["input"] is None:
-            rate = latest["rate"] if latest["active"] else 0.0
-            obj["input"] = latest["input"] + (obj["output"] - latest["output"]) * rate
-        tm.append(obj)
-        if adjust_previous and len(tm) > 1:
-            prev = tm[-2]
-            if prev["output"] < self.current_time:
-                rate = prev["rate"] if prev["active"] else 0.0
-                prev["input"] += (self.current_time - prev["output"]) * rate
-                prev["output"] = self.current_time
-            if obj["output"] != prev["output"]:  # (JavaScript would store Infinity / NaN here; a zero-length segment is never looked up)
-                prev["rate"] = (obj["input"] - prev["input"]) / (obj["output"] - prev["output"])
-        while len(tm) > 1 and tm[1]["output"] <= output_time:
-            tm.pop(0)
+        points = self.time_maps[s]
+        t_new = float(obj_in.get("outputTime", self.current_time))
+        # the map is ordered by output time.  The new point is derived from the earliest point it replaces (the worklet pops
+        # from the end and keeps the last one popped), or from the last point of the map if it replaces none
+        keep = [pt for pt in points if pt["output"] < t_new]
+        replaced = [pt for pt in points if pt["output"] >= t_new]
+        parent = replaced[0] if replaced else keep[-1]
+        fresh = dict(parent)
+        fresh["output"] = t_new
+        given = {k: v for k, v in obj_in.items() if k != "outputTime"}
+        fresh.update(given)
+        if given.get("input") is None:
+            speed = parent["rate"] if parent["active"] else 0.0
+            fresh["input"] = parent["input"] + (fresh["output"] - parent["output"]) * speed  # (`output` may have been given explicitly: stop(when))
+        points[:] = keep + [fresh]
+        if adjust_previous and len(points) >= 2:
+            before = points[-2]
+            now = self.current_time
+            if before["output"] < now:  # already playing: its remaining part starts now, from where it has got to
+                before["input"] += (now - before["output"]) * (before["rate"] if before["active"] else 0.0)
+                before["output"] = now
+            span = fresh["output"] - before["output"]
+            if span != 0:  # (a zero-length segment is never looked up; JavaScript would store Infinity there)
+                before["rate"] = (fresh["input"] - before["input"]) / span
+        # points that have been superseded by a later one at or before t_new are history
+        while len(points) > 1 and points[1]["output"] <= t_new:
+            del points[0]
         self._from_map(s)
-        return obj
+        return fresh
 
     def start(self, s, when=None, offset=0.0, duration=None, rate=1.0):  # :49-66
         obj = dict(active=True, input=offset, output=self.current_time + self.out_lat_s if when is None else when, rate=rate)

@@ -746,3 +746,70 @@ def test_live_batch_seek_every_quantum_bit_exact_vs_oracle(emu_libs, oracle_port
         else:
             assert np.array_equal(y[s], r), "stream %d: max diff %g" % (s, np.abs(y[s] - r).max())
     assert np.abs(y).max() > 0.05
+
+
+def test_live_time_map_semantics():
+    """The time-map bookkeeping of LiveBatch against the worklet's rules (web/web-wrapper.js:45-108,227-231,271-279),
+    on a stub engine: inheritance from the earliest replaced point, backwards extrapolation, stop = rate 0 from there on,
+    adjustPrevious re-aiming, loop wrap, and the window positions handed to the seek."""
+    from signalsmith_stretch_b200.live import LiveBatch
+
+    class Stub:
+        batch = 2
+
+        def __init__(self):
+            self.calls = []
+
+        def channels(self):
+            return 1
+
+        def inputLatency(self):
+            return 300
+
+        def outputLatency(self):
+            return 200
+
+        def seek(self, win, rates):
+            self.calls.append(("seek", win.copy(), np.array(rates)))
+
+        def process(self, x, n):
+            self.calls.append(("process", x.shape[-1], n))
+            return np.zeros((2, 1, n), np.float32)
+
+    sr = 1000.0
+    e = Stub()
+    lv = LiveBatch(e, sr)  # host mode (the stub has no bank)
+    ramp = np.arange(5000, dtype=np.float32)
+    lv.add_buffers(0, ramp)
+    lv.add_buffers(1, ramp)
+    a = lv.start(0, when=0.1, offset=2.0, rate=0.5)
+    assert (a["output"], a["input"], a["rate"], a["active"]) == (0.1, 2.0, 0.5, True)
+    b = lv.schedule(0, dict(outputTime=0.05, rate=2.0))  # replaces the point at 0.1: inherits from it, input extrapolated back
+    assert b["active"] is True and abs(b["input"] - (2.0 + (0.05 - 0.1) * 0.5)) < 1e-12 and b["rate"] == 2.0
+    assert [pt["output"] for pt in lv.time_maps[0]] == [0.05]  # (the worklet prunes up to the NEW point's time, :98-101)
+    c = lv.stop(0, when=1.0)  # position at the stop: 1.975 + 0.95 * 2
+    assert abs(c["input"] - (1.975 + 0.95 * 2.0)) < 1e-12 and c["active"] is False
+    d = lv.schedule(0, dict(outputTime=2.0))  # a stopped segment stands still
+    assert abs(d["input"] - c["input"]) < 1e-12
+    # (the worklet prunes the map up to the NEW point's output time, :98-101, so a point scheduled for the future becomes the
+    #  map's first entry at once and is looked up -- extrapolated backwards -- until its time comes: mirrored, quirk included)
+    assert [pt["output"] for pt in lv.time_maps[0]] == [2.0] and lv.time_maps[0][0]["active"] is False
+    # stream 1: play from 0 at rate 1, then a point "input 3.0 at output 2.0" with adjustPrevious
+    lv.start(1, when=0.0, offset=0.0, rate=1.0)
+    p = lv.schedule(1, dict(outputTime=2.0, input=3.0), adjust_previous=True)
+    assert p["rate"] == 1.0 and [pt["output"] for pt in lv.time_maps[1]] == [2.0]
+    # a quantum at current time 0: output time = 0.2 (output latency).  Stream 0 is stopped (silent window, rate 1); stream 1
+    # is on the line through (output 2.0, input 3.0) with rate 1: input 1.2 s, + input latency, window = the 500 samples before
+    lv.process(100)
+    kind, win, rates = e.calls[0]
+    assert kind == "seek" and e.calls[1] == ("process", 0, 100)
+    assert not win[0].any() and rates[0] == 1.0
+    end1 = int(np.floor((3.0 + (0.2 - 2.0) * 1.0 + 0.3) * sr + 0.5))
+    assert end1 == 1500 and np.array_equal(win[1, 0], ramp[end1 - 500:end1]) and rates[1] == 1.0
+    # loop: stream 1 loops [0.4, 0.6) s of its input; once past the end, the position wraps back by the loop length
+    lv.schedule(1, dict(loopStart=1.3, loopEnd=1.5))
+    for _ in range(6):
+        lv.process(100)
+    seg = lv.time_maps[1][0]
+    pos = lv._in[1] + (lv.current_time + 0.2 - seg["output"]) * seg["rate"]
+    assert 1.3 <= pos < 1.5 + 0.1
