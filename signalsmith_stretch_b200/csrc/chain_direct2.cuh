@@ -63,7 +63,9 @@ __device__ __forceinline__ void spin_pause() { __nanosleep(64); }
 
 __device__ __forceinline__ float2 sel2b(bool p, float2 a) { return make_float2(p ? a.x : 0.f, p ? a.y : 0.f); }
 
-template <int CT, int LT>
+// FAST (round 2; the default of the mono plain path, b200s_set_tuning key 3 = 1 selects the exact form): the fused
+// arithmetic of kernels.cuh (fmul_f, make_output_fast, ...), as the packed stereo kernel's fast mode.
+template <int CT, int LT, bool FAST = false>
 __global__ void __launch_bounds__(32 * CH2_MAXW) k_chain_direct2(Ctx x) {
 	const Cfg &g = x.cfg;
 	const int K = g.K;
@@ -202,17 +204,19 @@ __global__ void __launch_bounds__(32 * CH2_MAXW) k_chain_direct2(Ctx x) {
 					lo1 = spec_at(myIn, l1, K);
 					hi1 = spec_at(myIn, l1 + 1, K);
 				}
-				pv = xmul(pv, rotq); // :653-654 rotate Band::output and Band::prevInput by one interval
-				ro = xmul(ro, rotq);
-				const float e = xnorm(inq);                    // :679 (identity map: energy = |input|^2)
-				const float2 ph0 = xmul(ro, xmulc(inq, pv));   // :714-715
+				pv = FAST ? fmul_f(pv, rotq) : xmul(pv, rotq); // :653-654 rotate Band::output and Band::prevInput by one interval
+				ro = FAST ? fmul_f(ro, rotq) : xmul(ro, rotq);
+				const float e = FAST ? ffma(inq.x, inq.x, inq.y * inq.y) : xnorm(inq); // :679 (identity map: energy = |input|^2)
+				const float2 ph0 = FAST ? fmul_f(ro, fmulc_f(inq, pv)) : xmul(ro, xmulc(inq, pv)); // :714-715
 				const float den = fadd(fmaxf(re, e), B200S_NOISE_FLOOR);
-				const float2 newPre = sel2b(qIn, make_float2(fdivq(ph0.x, den), fdivq(ph0.y, den))); // :716
+				const float rden = FAST ? rcp_fast(den) : 0.f;
+				const float2 newPre = sel2b(qIn, FAST ? make_float2(ph0.x * rden, ph0.y * rden) : make_float2(fdivq(ph0.x, den), fdivq(ph0.y, den))); // :716
 				const float newE = qIn ? e : 0.f;
 				const float2 newIn = sel2b(qIn, inq);
-				const float2 newT2 = sel2b(qIn, xmulc(inq, xlerp2(lo2, hi2, f2))); // long twist at q (:758)
+				const float2 newT2 = sel2b(qIn, FAST ? fmulc_f(inq, flerp_f(lo2, hi2, f2)) : xmulc(inq, xlerp2(lo2, hi2, f2))); // long twist at q (:758)
 				// short twist at b+1 (:751,:771): Prediction::input[b+1] is inF[1] before the shift
-				const float2 t1N = xmulc(LT > 1 ? inF[LT > 1 ? 1 : 0] : newIn, xlerp2(lo1, hi1, f1));
+				const float2 in1 = LT > 1 ? inF[LT > 1 ? 1 : 0] : newIn;
+				const float2 t1N = FAST ? fmulc_f(in1, flerp_f(lo1, hi1, f1)) : xmulc(in1, xlerp2(lo1, hi1, f1));
 				{
 					const float2 rn = xmul(rotq, rotS);
 					rotq = make_float2(q >= 0 ? rn.x : rotq.x, q >= 0 ? rn.y : rotq.y);
@@ -233,11 +237,17 @@ __global__ void __launch_bounds__(32 * CH2_MAXW) k_chain_direct2(Ctx x) {
 				inF[LT - 1] = newIn;
 				// ---- main prediction at bin b (:727-800), this lane's channel as if it were the loudest
 				float2 phase = make_float2(0.f, 0.f);
-				phase = xadd(phase, sel2b(b > 0, xmul(oh[0], t1P)));               // :754
-				phase = xadd(phase, sel2b(b >= LT, xmul(oh[LT - 1], t2B)));        // :761
-				phase = xadd(phase, sel2b(b < K - 1, xmulc(pre[0], t1N)));         // :774
-				phase = xadd(phase, sel2b(b < K - LT, xmulc(pre[LT - 1], t2F[LT - 1]))); // :784
-				const float2 outOwn = make_output_q(phase, eB, inB);               // :788
+				if constexpr (FAST) { // the term that closes the recurrence (the previous bin's final) is added last
+					const float2 a = sel2b(b >= LT, fmul_f(oh[LT - 1], t2B)), bb = sel2b(b < K - 1, fmulc_f(pre[0], t1N));
+					const float2 cc = sel2b(b < K - LT, fmulc_f(pre[LT - 1], t2F[LT - 1])), dd = sel2b(b > 0, fmul_f(oh[0], t1P));
+					phase = make_float2(((a.x + bb.x) + cc.x) + dd.x, ((a.y + bb.y) + cc.y) + dd.y);
+				} else {
+					phase = xadd(phase, sel2b(b > 0, xmul(oh[0], t1P)));               // :754
+					phase = xadd(phase, sel2b(b >= LT, xmul(oh[LT - 1], t2B)));        // :761
+					phase = xadd(phase, sel2b(b < K - 1, xmulc(pre[0], t1N)));         // :774
+					phase = xadd(phase, sel2b(b < K - LT, xmulc(pre[LT - 1], t2F[LT - 1]))); // :784
+				}
+				const float2 outOwn = FAST ? make_output_fast(phase, eB, inB) : make_output_q(phase, eB, inB); // :788
 				float2 oc = outOwn;
 				if (CT > 1) { // the loudest channel wins (:729-737, first one on ties); the other is locked to it (:791-799)
 					const float eO = __shfl_xor_sync(0xffffffffu, eB, 1);
@@ -247,8 +257,8 @@ __global__ void __launch_bounds__(32 * CH2_MAXW) k_chain_direct2(Ctx x) {
 					outM.y = __shfl_xor_sync(0xffffffffu, outOwn.y, 1);
 					pinM.x = __shfl_xor_sync(0xffffffffu, inB.x, 1);
 					pinM.y = __shfl_xor_sync(0xffffffffu, inB.y, 1);
-					const float2 cph = xmul(outM, xmulc(inB, pinM)); // :796-797
-					const float2 other = make_output_q(cph, eB, inB);
+					const float2 cph = FAST ? fmul_f(outM, fmulc_f(inB, pinM)) : xmul(outM, xmulc(inB, pinM)); // :796-797
+					const float2 other = FAST ? make_output_fast(cph, eB, inB) : make_output_q(cph, eB, inB);
 					oc = make_float2(isMax ? outOwn.x : other.x, isMax ? outOwn.y : other.y);
 				}
 				// unconditional: out-of-range steps only produce values that every consumer masks

@@ -32,28 +32,9 @@ namespace b200s {
 // operation; both are tested against the oracle to the north-star tolerance (tests/test_gpu_parity.py).
 #ifdef B200S_EMU
 __device__ __forceinline__ f2 neg2(f2 a) { return f2{-a.a, -a.b}; }
-__device__ __forceinline__ float rcp_fast(float b) { return 1.0f / b; }
-__device__ __forceinline__ float rsqrt_fast(float b) { return 1.0f / std::sqrt(b); }
-__device__ __forceinline__ float sqrt_fast(float b) { return std::sqrt(b); }
-__device__ __forceinline__ float ffma(float a, float b, float c) { return std::fma(a, b, c); }
-#else
-__device__ __forceinline__ float rcp_fast(float b) {
-	float r;
-	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
-	return r;
-}
-__device__ __forceinline__ float rsqrt_fast(float b) {
-	float r;
-	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
-	return r;
-}
-__device__ __forceinline__ float sqrt_fast(float b) {
-	float r;
-	asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
-	return r;
-}
-__device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 #endif
+// (the scalar fast helpers -- rcp_fast, rsqrt_fast, sqrt_fast, ffma, fmul_f, fmulc_f, make_output_fast -- live in kernels.cuh:
+//  the mono direct chain uses them too)
 // a * b and a * conj(b), fused (4 packed instructions)
 __device__ __forceinline__ c2 fmul_c(c2 a, c2 b) {
 	return c2{fma2(a.re, b.re, neg2(mul2(a.im, b.im))), fma2(a.re, b.im, mul2(a.im, b.re))};
@@ -74,17 +55,6 @@ __device__ __forceinline__ c2 fmul_s(c2 a, float2 r) {
 }
 __device__ __forceinline__ f2 fnorm2(c2 a) { return fma2(a.re, a.re, mul2(a.im, a.im)); }
 __device__ __forceinline__ c2 flerp2(c2 lo, c2 hi, float fr) { return c2{fmas(hi.re - lo.re, fr, lo.re), fmas(hi.im - lo.im, fr, lo.im)}; }
-__device__ __forceinline__ float2 fmul_f(float2 a, float2 b) { return make_float2(ffma(a.x, b.x, -a.y * b.y), ffma(a.x, b.y, a.y * b.x)); }
-__device__ __forceinline__ float2 fmulc_f(float2 a, float2 b) { return make_float2(ffma(a.x, b.x, a.y * b.y), ffma(a.y, b.x, -a.x * b.y)); }
-// Prediction::makeOutput (:596-603)
-__device__ __forceinline__ float2 make_output_fast(float2 phase, float energy, float2 input) {
-	const float pn = ffma(phase.x, phase.x, phase.y * phase.y);
-	const bool weak = pn <= B200S_NOISE_FLOOR;
-	const float pni = ffma(input.x, input.x, input.y * input.y) + B200S_NOISE_FLOOR;
-	const float g = sqrt_fast(energy) * rsqrt_fast(weak ? pni : pn);
-	return make_float2((weak ? input.x : phase.x) * g, (weak ? input.y : phase.y) * g);
-}
-
 // Tiles of k_chain_direct4: as Chain3Tiles ([bin][lane] tiles, conflict-free for the per-step reads and for the
 // quarter-warp fill), without the output-row table (Band::output rows of consecutive blocks are equidistant).
 // (Measured dead end, profiles/r01_v13: lane-private rows filled with cp.async.bulk -- UBLKCP takes uniform operands,

@@ -249,20 +249,23 @@ static ChainKernel chain_kernel_for(int L, bool direct) {
 	}
 }
 // second-generation direct chain: lane = (block, channel), several warps per stream (chain_direct2.cuh)
-template <int CT>
+template <int CT, bool FAST>
 static ChainKernel chain2_kernel_for(int L) {
 	switch (L) {
-	case 1: return k_chain_direct2<CT, 1>;
-	case 2: return k_chain_direct2<CT, 2>;
-	case 3: return k_chain_direct2<CT, 3>;
-	case 4: return k_chain_direct2<CT, 4>;
-	case 5: return k_chain_direct2<CT, 5>;
-	case 6: return k_chain_direct2<CT, 6>;
-	case 7: return k_chain_direct2<CT, 7>;
-	default: return k_chain_direct2<CT, 8>;
+	case 1: return k_chain_direct2<CT, 1, FAST>;
+	case 2: return k_chain_direct2<CT, 2, FAST>;
+	case 3: return k_chain_direct2<CT, 3, FAST>;
+	case 4: return k_chain_direct2<CT, 4, FAST>;
+	case 5: return k_chain_direct2<CT, 5, FAST>;
+	case 6: return k_chain_direct2<CT, 6, FAST>;
+	case 7: return k_chain_direct2<CT, 7, FAST>;
+	default: return k_chain_direct2<CT, 8, FAST>;
 	}
 }
-static ChainKernel chain2_kernel(const Cfg &g) { return g.C == 1 ? chain2_kernel_for<1>(g.L) : chain2_kernel_for<2>(g.L); }
+// fast = the fused arithmetic (mono only: the stereo default is the packed kernel, whose exact cross-check this one is)
+static ChainKernel chain2_kernel(const Cfg &g, bool fast = false) {
+	return g.C == 1 ? (fast ? chain2_kernel_for<1, true>(g.L) : chain2_kernel_for<1, false>(g.L)) : chain2_kernel_for<2, false>(g.L);
+}
 // warps per stream for a call of nOut output samples: one per 32/C blocks (blocks trigger every H samples)
 static int chain2_warps(const Cfg &g, int nOut) {
 	const int blocks = (nOut + g.H - 1) / g.H, bpw = 32 / g.C;
@@ -539,6 +542,7 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	CK(cudaFuncSetAttribute(chain_kernel(g, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, false, true)));
 	CK(cudaFuncSetAttribute(chain_kernel(g, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, true)));
 	CK(cudaFuncSetAttribute(chain2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain2(g.C, CH2_MAXW)));
+	CK(cudaFuncSetAttribute(chain2_kernel(g, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain2(g.C, CH2_MAXW)));
 	if (g.L <= 4) { // seven two-warp CTAs of 30.6 KB per SM: ask for the full shared-memory carve-out
 		CK(cudaFuncSetAttribute(chain_ws_kernel<true>(g.L), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 		CK(cudaFuncSetAttribute(chain_ws_kernel<false>(g.L), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -794,7 +798,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 					PROF(PK_CHAIN, B200S_LAUNCH(chain3_kernel(g, chainV, !e->exactMath), dim3(x.sCount), dim3(32), chainV == 4 ? smem_chain4(g.L) : sizeof(Chain3Tiles), st, x));
 				} else if (plain && chainV == 2) {
 					const int W = chain2_warps(g, nOut);
-					ChainKernel kc = chain2_kernel(g);
+					ChainKernel kc = chain2_kernel(g, g.C == 1 && !e->exactMath);
 					PROF(PK_CHAIN, B200S_LAUNCH(kc, dim3(x.sCount), dim3(32 * W), smem_chain2(g.C, W), st, x));
 				} else {
 					dim3 grid((x.sCount + kChainWarps - 1) / kChainWarps), block(32 * kChainWarps);
