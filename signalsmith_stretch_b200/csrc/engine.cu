@@ -3,9 +3,13 @@
 // The host does no DSP: it sizes buffers, builds the constant tables once per configure() and
 // enqueues kernels on one CUDA stream.  Even the block scheduler runs on the device (k_plan), so
 // a process() call is a fixed, sync-free launch sequence:
-//     k_plan -> k_analyse[2] -> [k_pitch] -> [k_prep] -> k_chain[_direct{,2,3,4}] -> k_synth[2] -> k_commit
-// (the presets run the paired-FFT kernels of stft2.cuh and, stereo without frequency map / formants, k_chain_direct4;
-//  k_prep only for mapped / formant configurations, k_pitch only with setFormantBase(0))
+//   plain (no frequency map / formants), presets:  k_plan -> k_analyse2 -> k_chain_direct4 (stereo) | k_chain_direct2 (mono)
+//                                                  -> k_synth2 || k_commit (side stream)
+//   mapped / formants:  k_plan -> k_analyse2 -> [k_pitch] -> k_energy -> k_passes -> k_prep (map-only) -> k_products
+//                       -> k_chain_t -> k_synth2 || k_commit                                        (chain_t.cuh)
+//   calls that may stretch beyond 2x additionally launch k_prep + k_chain in random-only mode: they take the streams
+//   whose blocks draw random time factors (Call::hasRandom, decided per stream by k_plan); every other CTA exits at once
+//   generic sizes (not 3072 / 2560 bands): k_analyse / k_synth (fft.cuh) and the first-generation chains
 // Reference for every step: /root/reference/signalsmith-stretch.h (cited per kernel in kernels.cuh).
 #include <algorithm>
 #include <cmath>
