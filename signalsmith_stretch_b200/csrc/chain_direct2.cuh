@@ -130,6 +130,13 @@ __global__ void __launch_bounds__(32 * CH2_MAXW) k_chain_direct2(Ctx x) {
 		float2 rotq = rotOn ? rot0 : make_float2(1.f, 0.f); // rot[q] of the reference's float recurrence (:647-655)
 		const float2 rotS = rotOn ? rotStep : make_float2(1.f, 0.f);
 		const int steps = K + LT + D * (nAct - 1);
+		// first chunk start from which every lane (all active) has q - L*tf - 1 >= 0 and b = q - L >= L: q >= D*(BPW-1) + 2L + ceil(max L*tf) + 2
+		int interiorFrom = steps;
+		if (nAct == BPW) {
+			float mx = longTf;
+			for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+			interiorFrom = D * (BPW - 1) + 2 * LT + (int)ceilf(mx) + 2;
+		}
 		int chunk = 0;
 		for (int k0 = 0; k0 < steps; k0 += CHAIN_CH, ++chunk) {
 			// ---------------- flow control with the neighbouring warps ----------------
@@ -165,12 +172,14 @@ __global__ void __launch_bounds__(32 * CH2_MAXW) k_chain_direct2(Ctx x) {
 			cp_async_wait_all();
 			__syncwarp();
 			// ---------------- CHAIN_CH steps ----------------
-			auto step = [&](const int i, auto farTag) {
-				constexpr bool FAR = decltype(farTag)::value;
+			// INTERIOR (about nine chunks in ten of a full warp): every lane is active and all its bins and interpolation points
+			// lie inside [L, K) for the whole chunk, so the edge masks below are identities and are compiled out
+			auto step = [&](const int i, auto farTag, auto intTag) {
+				constexpr bool FAR = decltype(farTag)::value, INTERIOR = decltype(intTag)::value;
 				const int q = k0 + i - D * j;
 				const int b = q - LT;
-				const bool qIn = active && (unsigned)q < (unsigned)K;
-				const bool bIn = active && (unsigned)b < (unsigned)K;
+				const bool qIn = INTERIOR || (active && (unsigned)q < (unsigned)K);
+				const bool bIn = INTERIOR || (active && (unsigned)b < (unsigned)K);
 				// the twists need input interpolated at q - L*tf and (b+1) - tf  (:750,:757)
 				const float i2 = fsub((float)q, longTf);
 				const int l2 = (int)floorf(i2);
@@ -194,10 +203,10 @@ __global__ void __launch_bounds__(32 * CH2_MAXW) k_chain_direct2(Ctx x) {
 				float2 pv = U.pvy[i][lane];
 				float2 lo2, hi2, lo1, hi1;
 				if constexpr (!FAR) {
-					lo2 = sel2b(l2 >= 0, U.in[l2 & (CH2_RING - 1)][lane]);
-					hi2 = sel2b(l2 >= -1, U.in[(l2 + 1) & (CH2_RING - 1)][lane]);
-					lo1 = sel2b(l1 >= 0, U.in[l1 & (CH2_RING - 1)][lane]);
-					hi1 = sel2b(l1 >= -1, U.in[(l1 + 1) & (CH2_RING - 1)][lane]);
+					lo2 = sel2b(INTERIOR || l2 >= 0, U.in[l2 & (CH2_RING - 1)][lane]);
+					hi2 = sel2b(INTERIOR || l2 >= -1, U.in[(l2 + 1) & (CH2_RING - 1)][lane]);
+					lo1 = sel2b(INTERIOR || l1 >= 0, U.in[l1 & (CH2_RING - 1)][lane]);
+					hi1 = sel2b(INTERIOR || l1 >= -1, U.in[(l1 + 1) & (CH2_RING - 1)][lane]);
 				} else { // extreme stretch (> 2x): gather straight from the spectrum row
 					lo2 = spec_at(myIn, l2, K);
 					hi2 = spec_at(myIn, l2 + 1, K);
@@ -219,7 +228,7 @@ __global__ void __launch_bounds__(32 * CH2_MAXW) k_chain_direct2(Ctx x) {
 				const float2 t1N = FAST ? fmulc_f(in1, flerp_f(lo1, hi1, f1)) : xmulc(in1, xlerp2(lo1, hi1, f1));
 				{
 					const float2 rn = xmul(rotq, rotS);
-					rotq = make_float2(q >= 0 ? rn.x : rotq.x, q >= 0 ? rn.y : rotq.y);
+					rotq = make_float2((INTERIOR || q >= 0) ? rn.x : rotq.x, (INTERIOR || q >= 0) ? rn.y : rotq.y);
 				}
 				// ---- FIFO rotation (pure renaming after unrolling): what falls out belongs to bin b
 				const float eB = eF[0];
@@ -238,14 +247,14 @@ __global__ void __launch_bounds__(32 * CH2_MAXW) k_chain_direct2(Ctx x) {
 				// ---- main prediction at bin b (:727-800), this lane's channel as if it were the loudest
 				float2 phase = make_float2(0.f, 0.f);
 				if constexpr (FAST) { // the term that closes the recurrence (the previous bin's final) is added last
-					const float2 a = sel2b(b >= LT, fmul_f(oh[LT - 1], t2B)), bb = sel2b(b < K - 1, fmulc_f(pre[0], t1N));
-					const float2 cc = sel2b(b < K - LT, fmulc_f(pre[LT - 1], t2F[LT - 1])), dd = sel2b(b > 0, fmul_f(oh[0], t1P));
+					const float2 a = sel2b(INTERIOR || b >= LT, fmul_f(oh[LT - 1], t2B)), bb = sel2b(INTERIOR || b < K - 1, fmulc_f(pre[0], t1N));
+					const float2 cc = sel2b(INTERIOR || b < K - LT, fmulc_f(pre[LT - 1], t2F[LT - 1])), dd = sel2b(INTERIOR || b > 0, fmul_f(oh[0], t1P));
 					phase = make_float2(((a.x + bb.x) + cc.x) + dd.x, ((a.y + bb.y) + cc.y) + dd.y);
 				} else {
-					phase = xadd(phase, sel2b(b > 0, xmul(oh[0], t1P)));               // :754
-					phase = xadd(phase, sel2b(b >= LT, xmul(oh[LT - 1], t2B)));        // :761
-					phase = xadd(phase, sel2b(b < K - 1, xmulc(pre[0], t1N)));         // :774
-					phase = xadd(phase, sel2b(b < K - LT, xmulc(pre[LT - 1], t2F[LT - 1]))); // :784
+					phase = xadd(phase, sel2b(INTERIOR || b > 0, xmul(oh[0], t1P)));               // :754
+					phase = xadd(phase, sel2b(INTERIOR || b >= LT, xmul(oh[LT - 1], t2B)));        // :761
+					phase = xadd(phase, sel2b(INTERIOR || b < K - 1, xmulc(pre[0], t1N)));         // :774
+					phase = xadd(phase, sel2b(INTERIOR || b < K - LT, xmulc(pre[LT - 1], t2F[LT - 1]))); // :784
 				}
 				const float2 outOwn = FAST ? make_output_fast(phase, eB, inB) : make_output_q(phase, eB, inB); // :788
 				float2 oc = outOwn;
@@ -275,12 +284,15 @@ __global__ void __launch_bounds__(32 * CH2_MAXW) k_chain_direct2(Ctx x) {
 					UN.hoE[c][b & (CH2_HO - 1)] = eB;
 				}
 			};
-			if (!farAny) {
+			if (!farAny && k0 >= interiorFrom && k0 + CHAIN_CH <= K) {
 #pragma unroll
-				for (int i = 0; i < CHAIN_CH; ++i) step(i, std::false_type{});
+				for (int i = 0; i < CHAIN_CH; ++i) step(i, std::false_type{}, std::true_type{});
+			} else if (!farAny) {
+#pragma unroll
+				for (int i = 0; i < CHAIN_CH; ++i) step(i, std::false_type{}, std::false_type{});
 			} else {
 #pragma unroll 1
-				for (int i = 0; i < CHAIN_CH; ++i) step(i, std::true_type{});
+				for (int i = 0; i < CHAIN_CH; ++i) step(i, std::true_type{}, std::false_type{});
 			}
 			__syncwarp();
 			// ---------------- write the chunk's finals back, 64 B per row ----------------
