@@ -402,6 +402,8 @@ def run_sweep(args):
     batch = args.batch if args.batch != BATCH_PER_GPU else SWEEP_BATCH
     for preset in ("presetDefault", "presetCheaper"):
         for num, den in SWEEP_RATIOS:
+            if args.sweep_filter and args.sweep_filter not in "%s:%d/%d" % (preset, num, den):
+                continue
             eng = BatchStretch(batch, device=0)
             getattr(eng, preset)(1, float(SR))
             B, H, K = eng.blockSamples(), eng.intervalSamples(), eng.bands()
@@ -492,6 +494,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE config (default 2 = the headline; 5 = the ratio x preset sweep, one line per point)")
     ap.add_argument("--pcm16-probe", action="store_true", help="internal: child process measuring the 16-bit PCM boundary")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the child runs of BASELINE configs[2] / [3]")
+    ap.add_argument("--sweep-filter", default="", help="config 5: only the points whose 'preset:num/den' contains this string (e.g. presetDefault:5/4)")
     ap.add_argument("--live", action="store_true", help="the live / streaming caller (seek + process(0, 128) per quantum), batch 1024 stereo")
     args = ap.parse_args()
     if args.pcm16_probe:

@@ -55,7 +55,10 @@ int b200s_set_sub_batches(b200s_engine *e, int n);
  *   key 2: stream groups of the host-buffer pipeline in b200s_process (1..16, default 12)
  *   key 3: arithmetic of the stereo direct phase chain: 0 = fast (default: fused multiply-adds, SFU reciprocal / square
  *          root, as an optimising build of the reference), 1 = exact (the reference's unfused IEEE operation order;
- *          bit-identical to the CPU oracle when the FFT is substituted -- used by the tests) */
+ *          bit-identical to the CPU oracle when the FFT is substituted -- used by the tests)
+ *   key 0 values: 1..6 (4 = k_chain_direct4, 5 = warp-specialised, 6 = k_chain_direct6)
+ *   key 4: mapped / formant calls on the step-major path (1, default) or on the round-1 kernels (0)
+ *   key 5: mono plain calls: pairs of streams on the packed wavefront (1, default) or every stream on its own warp (0) */
 int b200s_set_tuning(b200s_engine *e, int key, int value);
 
 /* ---- configuration: presetDefault / presetCheaper / configure / reset  (:49-94) ---- */

@@ -52,7 +52,7 @@ def build_library(verbose=False):
 
     src = os.path.join(_HERE, "csrc", "engine.cu")
     out = library_path()
-    deps = [src] + [os.path.join(_HERE, "csrc", f) for f in ("kernels.cuh", "fft.cuh", "common.cuh", "chain_direct.cuh", "chain_direct2.cuh", "fft2.cuh", "stft2.cuh", "chain_direct3.cuh", "chain_direct4.cuh", "chain_ws.cuh", "chain_t.cuh")]
+    deps = [src] + [os.path.join(_HERE, "csrc", f) for f in ("kernels.cuh", "fft.cuh", "common.cuh", "chain_direct.cuh", "chain_direct2.cuh", "fft2.cuh", "stft2.cuh", "chain_direct3.cuh", "chain_direct4.cuh", "chain_ws.cuh", "chain_t.cuh", "chain_direct6.cuh")]
     deps.append(os.path.join(_ROOT, "include", "b200_stretch.h"))
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out

@@ -29,6 +29,7 @@
 #include "chain_direct3.cuh"
 #include "chain_direct4.cuh"
 #include "chain_ws.cuh"
+#include "chain_direct6.cuh"
 #include "chain_t.cuh"
 
 using namespace b200s;
@@ -91,6 +92,7 @@ struct b200s_engine {
 	float *dMapB = 0, *dMapG = 0, *dRatio = 0, *dTE = 0;
 	float2 *dTPI = 0, *dTFT = 0, *dTT1 = 0, *dTT2 = 0;
 	int tFrames = 0;
+	int dual = -1;     // b200s_set_tuning key 5: mono plain path, pairs of streams on the packed wavefront (-1: B200S_DUAL or on)
 	int stepMajor = 1; // b200s_set_tuning key 4: 0 = the round-1 kernels (k_prep + k_chain) for every stream
 	// random time factors beyond 2x stretch (:639-640): engine state per stream (lives as long as the handle, like the
 	// reference's randomEngine member), powers of the multiplier, the upwards twists of random blocks
@@ -313,7 +315,30 @@ static ChainKernel chain4_kernel(int L) {
 	default: return k_chain_direct4<8, FAST>;
 	}
 }
+template <bool FAST, bool DUAL>
+static ChainKernel chain6_kernel(int L) {
+	switch (L) {
+	case 1: return k_chain_direct6<1, FAST, DUAL>;
+	case 2: return k_chain_direct6<2, FAST, DUAL>;
+	case 3: return k_chain_direct6<3, FAST, DUAL>;
+	case 4: return k_chain_direct6<4, FAST, DUAL>;
+	case 5: return k_chain_direct6<5, FAST, DUAL>;
+	case 6: return k_chain_direct6<6, FAST, DUAL>;
+	case 7: return k_chain_direct6<7, FAST, DUAL>;
+	default: return k_chain_direct6<8, FAST, DUAL>;
+	}
+}
+// mono plain path: pairs of streams on the packed wavefront (k_chain_direct6<.., DUAL>) before k_chain_direct2; B200S_DUAL=0 switches it off (A/B)
+static bool dual_enabled() {
+	static int env = -1;
+	if (env < 0) {
+		const char *v = getenv("B200S_DUAL");
+		env = v ? (atoi(v) != 0) : 1;
+	}
+	return env != 0;
+}
 static ChainKernel chain3_kernel(const Cfg &g, int v, bool fast) {
+	if (v >= 6) return fast ? chain6_kernel<true, false>(g.L) : chain6_kernel<false, false>(g.L);
 	if (v >= 4) return fast ? chain4_kernel<true>(g.L) : chain4_kernel<false>(g.L);
 	switch (g.L) {
 	case 1: return k_chain_direct3<1>;
@@ -799,11 +824,22 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 					x.wsRan = 0;
 					if ((_rc = prof_mark(e, PK_CHAIN, false))) return _rc;
 				} else if (plain && chainV >= 3) {
-					PROF(PK_CHAIN, B200S_LAUNCH(chain3_kernel(g, chainV, !e->exactMath), dim3(x.sCount), dim3(32), chainV == 4 ? smem_chain4(g.L) : sizeof(Chain3Tiles), st, x));
+					PROF(PK_CHAIN, B200S_LAUNCH(chain3_kernel(g, chainV, !e->exactMath), dim3(x.sCount), dim3(32), chainV >= 6 ? smem_chain6() : chainV == 4 ? smem_chain4(g.L) : sizeof(Chain3Tiles), st, x));
 				} else if (plain && chainV == 2) {
 					const int W = chain2_warps(g, nOut);
 					ChainKernel kc = chain2_kernel(g, g.C == 1 && !e->exactMath);
-					PROF(PK_CHAIN, B200S_LAUNCH(kc, dim3(x.sCount), dim3(32 * W), smem_chain2(g.C, W), st, x));
+					int _rc;
+					if ((_rc = prof_mark(e, PK_CHAIN, true))) return _rc;
+					if (g.C == 1 && x.sCount >= 2 && (e->dual < 0 ? dual_enabled() : e->dual != 0)) { // pairs of mono streams that share their schedule: the packed wavefront
+						ChainKernel kd = e->exactMath ? chain6_kernel<false, true>(g.L) : chain6_kernel<true, true>(g.L);
+						B200S_LAUNCH(kd, dim3(x.sCount / 2), dim3(32), smem_chain6(), st, x);
+						CKL();
+						x.dualRan = 1; // k_chain_direct2 below: the pairs that do not, and the odd stream (every other CTA exits at once)
+					}
+					B200S_LAUNCH(kc, dim3(x.sCount), dim3(32 * W), smem_chain2(g.C, W), st, x);
+					CKL();
+					x.dualRan = 0;
+					if ((_rc = prof_mark(e, PK_CHAIN, false))) return _rc;
 				} else {
 					dim3 grid((x.sCount + kChainWarps - 1) / kChainWarps), block(32 * kChainWarps);
 					ChainKernel kc = chain_kernel(g, plain);
@@ -1057,11 +1093,12 @@ int b200s_set_sub_batches(b200s_engine *e, int n) {
 }
 int b200s_set_tuning(b200s_engine *e, int key, int value) {
 	if (!e) return B200S_EINVAL;
-	if (key == 0 && value >= 0 && value <= 5) e->chainV = value;
+	if (key == 0 && value >= 0 && value <= 6) e->chainV = value;
 	else if (key == 1 && (value == 0 || value == 1)) e->fftV1 = value;
 	else if (key == 2 && value >= 1) e->nHostParts = std::min(value, (int)b200s_engine::kMaxSub);
 	else if (key == 3 && (value == 0 || value == 1)) e->exactMath = value;
 	else if (key == 4 && (value == 0 || value == 1)) e->stepMajor = value;
+	else if (key == 5 && (value == 0 || value == 1)) e->dual = value;
 	else {
 		e->err = "b200s_set_tuning: unknown key or value";
 		return B200S_EINVAL;

@@ -287,7 +287,7 @@ def test_chain_kernel_generations_agree_bit_exactly(gpu, blocks_per_call):
     exercises the second group / the warp hand-off."""
     cfg, C, sr, ratio, kind = signals.CONFIGS["config2_stereo_0p8x"]
     outs = []
-    for gen in (1, 2, 3, 4, 5):
+    for gen in (1, 2, 3, 4, 5, 6):
         e = gpu(5)
         cfg(e)
         e.set_tuning(0, gen)
@@ -300,6 +300,28 @@ def test_chain_kernel_generations_agree_bit_exactly(gpu, blocks_per_call):
     assert np.array_equal(outs[0], outs[2]), "gen 3 differs: max %g" % np.abs(outs[0] - outs[2]).max()
     assert np.array_equal(outs[0], outs[3]), "gen 4 differs: max %g" % np.abs(outs[0] - outs[3]).max()
     assert np.array_equal(outs[0], outs[4]), "gen 5 (warp-specialised) differs: max %g" % np.abs(outs[0] - outs[4]).max()
+    assert np.array_equal(outs[0], outs[5]), "gen 6 (product FIFOs, shared-memory hand-off) differs: max %g" % np.abs(outs[0] - outs[5]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset,ratio", [("presetDefault", 0.8), ("presetCheaper", 2.0)])
+def test_mono_stream_pairs_agree_with_one_stream_per_warp_bit_exactly(gpu, preset, ratio):
+    """Mono plain path: pairs of streams on the packed wavefront (k_chain_direct6<.., DUAL>; stream 4 of the five stays on
+    k_chain_direct2, and so does the pair (2, 3) while stream 3 is silent) against every stream on k_chain_direct2, exact
+    arithmetic: identical bit for bit.  40 blocks per call: a second group of lanes."""
+    outs = []
+    for dual in (0, 1):
+        e = gpu(5)
+        getattr(e, preset)(1, 48000.0)
+        e.set_tuning(3, 1)
+        e.set_tuning(5, dual)
+        H = e.intervalSamples()
+        n_out = 3 * 40 * H
+        x = signals.batch("harmonic", 5, 1, int(round(n_out / ratio)), 48000)
+        x[3, :, x.shape[-1] // 3: x.shape[-1] // 2] = 0.0
+        outs.append(signals.run_batch(e, x, ratio, 40 * H))
+    assert np.abs(outs[0]).max() > 0.1
+    assert np.array_equal(outs[0], outs[1]), "max %g" % np.abs(outs[0] - outs[1]).max()
 
 
 @pytest.mark.gpu

@@ -61,11 +61,13 @@ def test_product_sources_never_touch_the_oracle():
 
 
 # ------------------------------------------------------------------ kernels under the emulator
-def _emu(path, batch, exact_math=True):
+def _emu(path, batch, exact_math=True, gen=0):
     from signalsmith_stretch_b200 import BatchStretch
 
     e = BatchStretch(batch, lib_path=path)
     e.set_tuning(3, 1 if exact_math else 0)  # the bit-exact checks run the phase chain in the reference's own arithmetic
+    if gen:
+        e.set_tuning(0, gen)  # generation of the stereo direct chain kernel (0 = the default)
     return e
 
 
@@ -413,6 +415,80 @@ def test_randomised_configurations_bit_exact_vs_oracle(emu_libs, oracle_port):
         y = signals.run_batch(g, x, ratio, chunk)
         ref = _oracle_batch(oracle_port, cfg, x, ratio, chunk)
         assert np.array_equal(y, ref), (it, preset, C, sr, split, ratio, semis, ton, form, chunk, float(np.abs(y - ref).max()))
+
+
+@pytest.mark.parametrize("gen", [4, 6])
+@pytest.mark.parametrize("idx", [0, 3, 4, 5])
+def test_stereo_chain_generations_bit_exact_vs_oracle(emu_libs, oracle_port, gen, idx):
+    """Both packed stereo chain kernels (k_chain_direct4 and its leaner successor k_chain_direct6, which forms the twists
+    one / two bins behind the preliminary prediction, keeps products instead of factors in its FIFOs and hands the finals
+    from lane to lane through shared memory), selected explicitly: aligned calls, all 32 lanes busy, odd lane skew (L = 3),
+    and more than 32 blocks per call (a second group of lanes continuing from the rows the first group wrote)."""
+    name, cfg, C, ratio, n, chunk = PRESET_CALLS[idx]
+    assert C == 2
+    x = signals.batch("harmonic", 2, C, n, 48000)
+    g = _emu(emu_libs["exact"], 2, gen=gen)
+    cfg(g)
+    y = signals.run_batch(g, x, ratio, chunk)
+    ref = _oracle_batch(oracle_port, cfg, x, ratio, chunk)
+    assert np.array_equal(y, ref), "%s gen %d: max diff %g" % (name, gen, np.abs(y - ref).max())
+
+
+def test_stereo_chain_generation6_with_diverging_streams_and_silence(emu_libs, oracle_port):
+    S, C, calls, n = 3, 2, 7, 5760
+    x = signals.batch("harmonic", S, C, calls * n, 48000)
+    x[1, :, 2 * n:5 * n] = 0.0
+    g = _emu(emu_libs["exact"], S, gen=6)
+    g.presetDefault(C, 48000.0)
+    y = signals.run_batch(g, x, 0.8, int(n * 0.8))
+    ref = _oracle_batch(oracle_port, lambda o: o.presetDefault(C, 48000.0), x, 0.8, int(n * 0.8))
+    assert np.array_equal(y, ref), "max diff %g" % np.abs(y - ref).max()
+
+
+MONO_PAIRS = [
+    # mono plain calls: pairs of streams run on the packed wavefront (k_chain_direct6<.., DUAL>), the odd stream of the
+    # batch and pairs whose schedules differ on k_chain_direct2.  (block, interval) -> long vertical step L = 1 .. 8
+    ("L1", 256, 256, 0.8), ("L2", 512, 256, 1.25), ("L3", 384, 128, 0.8), ("L4", 512, 128, 0.5), ("L5", 500, 100, 1.6), ("L8", 512, 64, 0.8),
+]
+
+
+@pytest.mark.parametrize("name,B,H,ratio", MONO_PAIRS, ids=[c[0] for c in MONO_PAIRS])
+def test_mono_stream_pairs_on_the_packed_chain_bit_exact_vs_oracle(emu_libs, oracle_port, name, B, H, ratio):
+    S = 5  # two pairs and an odd stream
+    x = signals.batch("harmonic", S, 1, 12 * B, 48000)
+    x[3, :, 3 * B:7 * B] = 0.0  # stream 3 falls silent for a while: the pair (2, 3) stops sharing its schedule
+    g = _emu(emu_libs["exact"], S)
+    g.configure(1, B, H)
+    chunk = 40 * H + 17  # more than 32 blocks per call: a second group of lanes
+    y = signals.run_batch(g, x, ratio, chunk)
+    ref = _oracle_batch(oracle_port, lambda o: o.configure(1, B, H), x, ratio, chunk)
+    for s_ in range(S):
+        assert np.array_equal(y[s_], ref[s_]), "stream %d: max diff %g" % (s_, np.abs(y[s_] - ref[s_]).max())
+
+
+def test_mono_stream_pairs_at_preset_size_bit_exact_vs_oracle(emu_libs, oracle_port):
+    for cfg, ratio, n, chunk in ((lambda o: o.presetDefault(1, 48000.0), 0.8, 2 * 57600, 46080), (lambda o: o.presetCheaper(1, 48000.0), 2.0, 30000, 20000)):
+        x = signals.batch("harmonic", 2, 1, n, 48000)
+        g = _emu(emu_libs["exact"], 2)
+        cfg(g)
+        y = signals.run_batch(g, x, ratio, chunk)
+        ref = _oracle_batch(oracle_port, cfg, x, ratio, chunk)
+        assert np.array_equal(y, ref), "max diff %g" % np.abs(y - ref).max()
+
+
+def test_fast_chain_arithmetic_of_generation6_and_of_mono_pairs_stays_within_tolerance(emu_libs, oracle_port):
+    cases = [(PRESET_CALLS[3], 6), (PRESET_CALLS[4], 6), (("default_mono_0.8x", lambda o: o.presetDefault(1, 48000.0), 1, 0.8, 2 * 57600, 46080), 0)]
+    for (name, cfg, C, ratio, n, chunk), gen in cases:
+        x = signals.batch("harmonic", 2, C, n, 48000)
+        g = _emu(emu_libs["exact"], 2, exact_math=False, gen=gen)
+        cfg(g)
+        y = signals.run_batch(g, x, ratio, chunk)
+        ref = _oracle_batch(oracle_port, cfg, x, ratio, chunk)
+        assert not np.array_equal(y, ref), name
+        H = g.intervalSamples()
+        head = g.outputLatency() + int(g.inputLatency() * ratio) + 8 * H
+        assert rms((y - ref)[..., :head]) <= 2e-6, (name, rms((y - ref)[..., :head]))
+        assert rms(y - ref) <= 1e-3, (name, rms(y - ref))
 
 
 def test_fast_chain_arithmetic_stays_within_tolerance(emu_libs, oracle_port):
