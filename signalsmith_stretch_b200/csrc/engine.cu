@@ -231,7 +231,14 @@ static int prof_mark(b200s_engine *e, int kind, bool begin) {
 	} while (0)
 
 typedef void (*ChainKernel)(Ctx);
+// Superseded kernel generations (first-generation FFT kernels specialised for the preset sizes, chain generations 1, 3 and 5)
+// are only instantiated with -DB200S_KEEP_OLD_KERNELS (the emulator test builds: cross-checks between generations); the
+// shipped library carries the generic FFT kernels (any size), k_chain (any configuration), k_chain_direct2 / 4 / 6, k_chain_t.
+#ifdef B200S_KEEP_OLD_KERNELS
 static ChainKernel analyse_kernel(const Cfg &g) { return g.K == 3072 ? k_analyse<3072> : g.K == 2560 ? k_analyse<2560> : k_analyse<0>; }
+#else
+static ChainKernel analyse_kernel(const Cfg &) { return k_analyse<0>; }
+#endif
 // paired in-place FFT kernels (stft2.cuh) for the preset sizes
 static bool use_pair_fft(const Cfg &g, int forceV1 = 0) {
 	static int v1 = -1;
@@ -240,18 +247,35 @@ static bool use_pair_fft(const Cfg &g, int forceV1 = 0) {
 }
 static ChainKernel analyse2_kernel(const Cfg &g) { return g.K == 3072 ? k_analyse2<3072> : k_analyse2<2560>; }
 static ChainKernel synth2_kernel(const Cfg &g) { return g.K == 3072 ? k_synth2<3072> : k_synth2<2560>; }
+#ifdef B200S_KEEP_OLD_KERNELS
 static ChainKernel synth_kernel(const Cfg &g) { return g.K == 3072 ? k_synth<3072> : g.K == 2560 ? k_synth<2560> : k_synth<0>; }
+#else
+static ChainKernel synth_kernel(const Cfg &) { return k_synth<0>; }
+#endif
 template <int CT>
 static ChainKernel chain_kernel_for(int L, bool direct) {
+#ifdef B200S_KEEP_OLD_KERNELS
+	if (direct) switch (L) {
+		case 1: return k_chain_direct<CT, 1>;
+		case 2: return k_chain_direct<CT, 2>;
+		case 3: return k_chain_direct<CT, 3>;
+		case 4: return k_chain_direct<CT, 4>;
+		case 5: return k_chain_direct<CT, 5>;
+		case 6: return k_chain_direct<CT, 6>;
+		case 7: return k_chain_direct<CT, 7>;
+		default: return k_chain_direct<CT, 8>;
+		}
+#endif
+	(void)direct; // (without the old generations chain_version() never asks for the first-generation direct kernel)
 	switch (L) {
-	case 1: return direct ? k_chain_direct<CT, 1> : k_chain<CT, 1, false>;
-	case 2: return direct ? k_chain_direct<CT, 2> : k_chain<CT, 2, false>;
-	case 3: return direct ? k_chain_direct<CT, 3> : k_chain<CT, 3, false>;
-	case 4: return direct ? k_chain_direct<CT, 4> : k_chain<CT, 4, false>;
-	case 5: return direct ? k_chain_direct<CT, 5> : k_chain<CT, 5, false>;
-	case 6: return direct ? k_chain_direct<CT, 6> : k_chain<CT, 6, false>;
-	case 7: return direct ? k_chain_direct<CT, 7> : k_chain<CT, 7, false>;
-	default: return direct ? k_chain_direct<CT, 8> : k_chain<CT, 8, false>;
+	case 1: return k_chain<CT, 1, false>;
+	case 2: return k_chain<CT, 2, false>;
+	case 3: return k_chain<CT, 3, false>;
+	case 4: return k_chain<CT, 4, false>;
+	case 5: return k_chain<CT, 5, false>;
+	case 6: return k_chain<CT, 6, false>;
+	case 7: return k_chain<CT, 7, false>;
+	default: return k_chain<CT, 8, false>;
 	}
 }
 // second-generation direct chain: lane = (block, channel), several warps per stream (chain_direct2.cuh)
@@ -290,9 +314,14 @@ static int chain_version(const Cfg &g, int override, int forceFftV1) {
 	int want = override ? override : env ? env : 4;
 	if (want >= 3 && !(g.C == 2 && use_pair_fft(g, forceFftV1))) want = 2;
 	if (want == 5 && g.L > 4) want = 4; // k_chain_ws is laid out for L <= 4 (both presets)
+#ifndef B200S_KEEP_OLD_KERNELS
+	if (want == 1) want = 2;
+	if (want == 3 || want == 5) want = 4;
+#endif
 	return want;
 }
 // 5 = warp-specialised producer / consumer chain (chain_ws.cuh), followed by k_chain_direct4 for the streams it leaves
+#ifdef B200S_KEEP_OLD_KERNELS
 template <bool FAST>
 static ChainKernel chain_ws_kernel(int L) {
 	switch (L) {
@@ -302,6 +331,7 @@ static ChainKernel chain_ws_kernel(int L) {
 	default: return k_chain_ws<4, FAST>;
 	}
 }
+#endif
 template <bool FAST>
 static ChainKernel chain4_kernel(int L) {
 	switch (L) {
@@ -340,6 +370,7 @@ static bool dual_enabled() {
 static ChainKernel chain3_kernel(const Cfg &g, int v, bool fast) {
 	if (v >= 6) return fast ? chain6_kernel<true, false>(g.L) : chain6_kernel<false, false>(g.L);
 	if (v >= 4) return fast ? chain4_kernel<true>(g.L) : chain4_kernel<false>(g.L);
+#ifdef B200S_KEEP_OLD_KERNELS
 	switch (g.L) {
 	case 1: return k_chain_direct3<1>;
 	case 2: return k_chain_direct3<2>;
@@ -350,6 +381,9 @@ static ChainKernel chain3_kernel(const Cfg &g, int v, bool fast) {
 	case 7: return k_chain_direct3<7>;
 	default: return k_chain_direct3<8>;
 	}
+#else
+	return fast ? chain4_kernel<true>(g.L) : chain4_kernel<false>(g.L);
+#endif
 }
 template <int CT>
 static ChainKernel chain_t_kernel_for(int L) {
@@ -572,10 +606,15 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	CK(cudaFuncSetAttribute(chain_kernel(g, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, true)));
 	CK(cudaFuncSetAttribute(chain2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain2(g.C, CH2_MAXW)));
 	CK(cudaFuncSetAttribute(chain2_kernel(g, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain2(g.C, CH2_MAXW)));
+#ifdef B200S_KEEP_OLD_KERNELS
 	if (g.L <= 4) { // seven two-warp CTAs of 30.6 KB per SM: ask for the full shared-memory carve-out
 		CK(cudaFuncSetAttribute(chain_ws_kernel<true>(g.L), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 		CK(cudaFuncSetAttribute(chain_ws_kernel<false>(g.L), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 	}
+#endif
+	// k_chain_direct6: seven one-warp CTAs of 31.5 KB per SM need the full shared-memory carve-out
+	CK(cudaFuncSetAttribute(g.C == 1 ? chain6_kernel<true, true>(g.L) : chain6_kernel<true, false>(g.L), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+	CK(cudaFuncSetAttribute(g.C == 1 ? chain6_kernel<false, true>(g.L) : chain6_kernel<false, false>(g.L), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 	if (use_pair_fft(g)) {
 		CK(cudaFuncSetAttribute(analyse2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_analyse2(g)));
 		CK(cudaFuncSetAttribute(synth2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_synth2(g)));
@@ -811,6 +850,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 						x.randomOnly = 0;
 					}
 					if ((_rc = prof_mark(e, PK_CHAIN, false))) return _rc;
+#ifdef B200S_KEEP_OLD_KERNELS
 				} else if (plain && chainV == 5) {
 					int _rc;
 					if ((_rc = prof_mark(e, PK_CHAIN, true))) return _rc;
@@ -823,6 +863,7 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 					CKL();
 					x.wsRan = 0;
 					if ((_rc = prof_mark(e, PK_CHAIN, false))) return _rc;
+#endif
 				} else if (plain && chainV >= 3) {
 					PROF(PK_CHAIN, B200S_LAUNCH(chain3_kernel(g, chainV, !e->exactMath), dim3(x.sCount), dim3(32), chainV >= 6 ? smem_chain6() : chainV == 4 ? smem_chain4(g.L) : sizeof(Chain3Tiles), st, x));
 				} else if (plain && chainV == 2) {
@@ -1093,7 +1134,15 @@ int b200s_set_sub_batches(b200s_engine *e, int n) {
 }
 int b200s_set_tuning(b200s_engine *e, int key, int value) {
 	if (!e) return B200S_EINVAL;
-	if (key == 0 && value >= 0 && value <= 6) e->chainV = value;
+	if (key == 0 && value >= 0 && value <= 6) {
+#ifndef B200S_KEEP_OLD_KERNELS
+		if (value == 1 || value == 3 || value == 5) {
+			e->err = "b200s_set_tuning: chain generations 1, 3 and 5 are superseded and not part of this build (-DB200S_KEEP_OLD_KERNELS)";
+			return B200S_EUNSUPPORTED;
+		}
+#endif
+		e->chainV = value;
+	}
 	else if (key == 1 && (value == 0 || value == 1)) e->fftV1 = value;
 	else if (key == 2 && value >= 1) e->nHostParts = std::min(value, (int)b200s_engine::kMaxSub);
 	else if (key == 3 && (value == 0 || value == 1)) e->exactMath = value;

@@ -287,20 +287,25 @@ def test_chain_kernel_generations_agree_bit_exactly(gpu, blocks_per_call):
     exercises the second group / the warp hand-off."""
     cfg, C, sr, ratio, kind = signals.CONFIGS["config2_stereo_0p8x"]
     outs = []
+    from signalsmith_stretch_b200 import StretchError
+
+    gens = []
     for gen in (1, 2, 3, 4, 5, 6):
         e = gpu(5)
         cfg(e)
-        e.set_tuning(0, gen)
+        try:
+            e.set_tuning(0, gen)
+        except StretchError:  # generations 1, 3, 5 are superseded: only in builds with -DB200S_KEEP_OLD_KERNELS
+            continue
+        gens.append(gen)
         e.set_tuning(3, 1)  # exact arithmetic: generation 4 defaults to the fast (fused) mode
         H = e.intervalSamples()
         n_out = 3 * blocks_per_call * H
         x = signals.batch(kind, 5, C, int(round(n_out / ratio)), sr)
         outs.append(signals.run_batch(e, x, ratio, blocks_per_call * H))
-    assert np.array_equal(outs[0], outs[1]), "gen 2 differs: max %g" % np.abs(outs[0] - outs[1]).max()
-    assert np.array_equal(outs[0], outs[2]), "gen 3 differs: max %g" % np.abs(outs[0] - outs[2]).max()
-    assert np.array_equal(outs[0], outs[3]), "gen 4 differs: max %g" % np.abs(outs[0] - outs[3]).max()
-    assert np.array_equal(outs[0], outs[4]), "gen 5 (warp-specialised) differs: max %g" % np.abs(outs[0] - outs[4]).max()
-    assert np.array_equal(outs[0], outs[5]), "gen 6 (product FIFOs, shared-memory hand-off) differs: max %g" % np.abs(outs[0] - outs[5]).max()
+    assert {2, 4, 6} <= set(gens), gens
+    for gen, out in zip(gens[1:], outs[1:]):
+        assert np.array_equal(outs[0], out), "generation %d differs from generation %d: max %g" % (gen, gens[0], np.abs(outs[0] - out).max())
 
 
 @pytest.mark.gpu
