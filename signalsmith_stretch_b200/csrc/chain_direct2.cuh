@@ -66,7 +66,7 @@ __device__ __forceinline__ float2 sel2b(bool p, float2 a) { return make_float2(p
 // k_chain_direct6<.., DUAL> (chain_direct6.cuh) packs two mono streams into one warp.  It needs both streams of the pair
 // starting at stream s (s - sBase even) to be there, free of random blocks, and to walk the same schedule in this call --
 // same blocks, flags, time factors and spectrum slots (streams of a batch do, unless one of them was silent or sought
-// differently).  Evaluated identically by both kernels: pairs that fail are run by k_chain_direct2 one stream at a time.
+// differently).  Pairs that fail run one stream at a time (the stream in both halves).
 __device__ __forceinline__ bool dual_pair_ok(const Ctx &x, int s, int lane) {
 	if (s + 1 >= x.sBase + x.sCount) return false;
 	const Call a = x.call[s], b = x.call[s + 1];
@@ -95,7 +95,6 @@ __global__ void __launch_bounds__(32 * CH2_MAXW) k_chain_direct2(Ctx x) {
 	const Call cl = x.call[s];
 	if (cl.nFrames == 0) return;
 	if (cl.hasRandom && x.randomPathOn) return; // a block beyond 2x stretch draws random time factors: k_prep + k_chain take the stream
-	if (x.dualRan && dual_pair_ok(x, x.sBase + ((s - x.sBase) & ~1), lane)) return; // k_chain_direct6<.., DUAL> has done this pair
 	Chain2Sync &SY = *(Chain2Sync *)dyn_smem;
 	Chain2Tiles<CT> &U = ((Chain2Tiles<CT> *)((char *)dyn_smem + 64))[warp];
 	Chain2Tiles<CT> &UN = ((Chain2Tiles<CT> *)((char *)dyn_smem + 64))[warp + 1 < nWarps ? warp + 1 : warp]; // successor's tiles

@@ -59,20 +59,32 @@ __device__ __forceinline__ float2 make_output_fast_e(float2 phase, float energy,
 	return make_float2((weak ? input.x : phase.x) * g, (weak ? input.y : phase.y) * g);
 }
 
+// Ask L2 for `bytes` (a multiple of 16) at a 16-byte aligned global address: ONE request for a long contiguous piece of a
+// spectrum row.  The chain's own accesses are 128-byte (stereo) / 64-byte (mono) pieces of 32+ different rows per warp and
+// chunk; measured (round 3: the kernel's time follows its bytes, not its instructions -- generation 6 with 11 % fewer
+// instructions ran no faster, two mono streams per warp no faster than one) that scattered pattern, not issue or latency,
+// bounds the chain beyond ~500 streams.  The chunk fills then hit L2.
+__device__ __forceinline__ void l2_prefetch_bulk(const void *p, unsigned bytes) {
+#ifndef B200S_EMU
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#else
+	(void)p;
+	(void)bytes;
+#endif
+}
+
 template <int LT, bool FAST, bool DUAL>
 __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 	const Cfg &g = x.cfg;
 	const int K = g.K;
 	B200S_DYN_SHARED
 	const int lane = threadIdx.x & 31;
-	const int s = x.sBase + (DUAL ? 2 : 1) * blockIdx.x; // DUAL: stream s in the low halves, stream s + 1 in the high halves
-	if constexpr (DUAL) {
-		if (!dual_pair_ok(x, s, lane)) return; // k_chain_direct2 takes these streams one by one
-	}
-	const Call cl = x.call[s];
-	if (cl.nFrames == 0) return;
-	if (cl.hasRandom && x.randomPathOn) return; // a block beyond 2x stretch draws random time factors: k_prep + k_chain take the stream
-	const int sH[2] = {s, s + 1};
+	// DUAL: CTA p owns streams s0 = sBase + 2p and s0 + 1.  When they share their schedule (dual_pair_ok) they run packed,
+	// stream s0 in the low halves and s0 + 1 in the high halves; otherwise (and for the odd stream of an odd batch) each
+	// runs alone with itself in both halves, one after the other -- every mono stream goes through the same arithmetic.
+	const int s0 = x.sBase + (DUAL ? 2 : 1) * blockIdx.x;
+	const bool pairOk = DUAL && dual_pair_ok(x, s0, lane);
+	const int nPass = (DUAL && !pairOk && s0 + 1 < x.sBase + x.sCount) ? 2 : 1;
 	constexpr int G = LT + 2; // lane skew in bins
 	static_assert(G + 1 <= CH6_ER && 2 * CHAIN_CH <= CH6_ER, "energy ring too short");
 	Chain6Tiles &U = *(Chain6Tiles *)dyn_smem;
@@ -83,6 +95,12 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 	const f2 z2 = f2_make(0.f, 0.f);
 	const c2 zc = c2{z2, z2};
 
+	for (int pass = 0; pass < nPass; ++pass) {
+	const int s = s0 + pass;
+	const Call cl = x.call[s];
+	if (cl.nFrames == 0) continue;
+	if (cl.hasRandom && x.randomPathOn) continue; // a block beyond 2x stretch draws random time factors: k_prep + k_chain take the stream
+	const int sH[2] = {s, pairOk ? s + 1 : s};
 	for (int base = 0; base < cl.nFrames; base += 32) {
 		__syncwarp();
 		const int f = base + lane;
@@ -112,7 +130,8 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 		// (DUAL: k_commit of the mono path reads the last block's row of cE, written below)
 		const int prevSlotIn = base == 0 ? 0 : x.frames[(size_t)s * x.maxFrames + base - 1].inSlot;
 		const float4 *prevInIl = nullptr, *myInIl = nullptr;
-		const float2 *prevInD[2] = {nullptr, nullptr}, *myInD[2] = {nullptr, nullptr};
+		const float2 *prevInD[2] = {nullptr, nullptr}, *myInD[2] = {nullptr, nullptr}, *myPvD[2] = {nullptr, nullptr};
+		const float4 *myPvIl = nullptr;
 		float2 *yBaseD[2] = {nullptr, nullptr};
 		float *eRowD[2] = {nullptr, nullptr};
 		float2 *yBase = nullptr;
@@ -122,7 +141,8 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 				prevInD[h] = base == 0 ? nullptr : spec_slot(x, sH[h], prevSlotIn, 0);
 				myInD[h] = spec_slot(x, sH[h], fr.inSlot, 0);
 				U.rowIn[h][lane] = myInD[h];
-				U.rowPv[h][lane] = spec_slot(x, sH[h], fr.prevSlot, 0);
+				myPvD[h] = spec_slot(x, sH[h], fr.prevSlot, 0);
+				U.rowPv[h][lane] = myPvD[h];
 				yBaseD[h] = x.Y + coef_off(x, sH[h], base, 0); // Band::output row of block base + r of stream h: yBaseD[h] + r * K
 				eRowD[h] = x.cE + coef_off(x, sH[h], active ? f : base, 0);
 			}
@@ -130,7 +150,8 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 			prevInIl = base == 0 ? nullptr : il_row(x, s, prevSlotIn);
 			myInIl = il_row(x, s, fr.inSlot);
 			U.rowIn[0][lane] = myInIl;
-			U.rowPv[0][lane] = il_row(x, s, fr.prevSlot);
+			myPvIl = il_row(x, s, fr.prevSlot);
+			U.rowPv[0][lane] = myPvIl;
 			yBase = x.Y + coef_off(x, s, base, 0); // Band::output row of block base + r, channel c: yBase + (2r + c) * K
 		}
 		const bool lastFrame = DUAL && active && f == cl.nFrames - 1; // its Prediction::energy is the state the next call continues from
@@ -172,6 +193,20 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 		// reads, for step i+1, the slot before its own row), energies of bins kf .. kf+7 into the padding before rows
 		// [bin & 15] of eR.  None of these slots is read by the chunk in progress (other buffer / other half of the ring).
 		auto fill = [&](int kf, int buf) {
+			if (x.l2pf > 0 && (kf & (x.l2pf - 1)) == 0) { // every l2pf bins (a power of two >= 8): this lane's own rows, the l2pf bins after those staged next
+				const int q0 = max(kf + x.l2pf - G * lane, 0), q1 = min(kf + 2 * x.l2pf - G * lane, K);
+				if (active && q1 > q0) {
+					if constexpr (DUAL) {
+						for (int h = 0; h < (pairOk ? 2 : 1); ++h) {
+							l2_prefetch_bulk(myInD[h] + q0, 8u * (unsigned)(q1 - q0));
+							l2_prefetch_bulk(myPvD[h] + q0, 8u * (unsigned)(q1 - q0));
+						}
+					} else {
+						l2_prefetch_bulk(myInIl + q0, 16u * (unsigned)(q1 - q0));
+						l2_prefetch_bulk(myPvIl + q0, 16u * (unsigned)(q1 - q0));
+					}
+				}
+			}
 			if constexpr (DUAL) {
 				const float2 *rIn[2][8], *rPv[2][8];
 #pragma unroll
@@ -459,6 +494,8 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 			__syncwarp();
 		}
 	}
+	__syncwarp();
+	} // pass
 }
 
 static inline size_t smem_chain6() { return sizeof(Chain6Tiles); }

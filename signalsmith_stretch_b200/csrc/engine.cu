@@ -36,6 +36,7 @@ using namespace b200s;
 
 static std::string g_createError;
 
+#define B200S_L2PF_DEFAULT 0 // bins per bulk L2 prefetch in k_chain_direct6 (0 = off)
 struct b200s_engine {
 	int S = 0, device = 0;
 	long seed = 0;
@@ -92,6 +93,7 @@ struct b200s_engine {
 	float *dMapB = 0, *dMapG = 0, *dRatio = 0, *dTE = 0;
 	float2 *dTPI = 0, *dTFT = 0, *dTT1 = 0, *dTT2 = 0;
 	int tFrames = 0;
+	int l2pf = -1;     // b200s_set_tuning key 6: k_chain_direct6, bins per bulk L2 prefetch of a spectrum row (0 = off; -1: B200S_L2PF or the default)
 	int dual = -1;     // b200s_set_tuning key 5: mono plain path, pairs of streams on the packed wavefront (-1: B200S_DUAL or on)
 	int stepMajor = 1; // b200s_set_tuning key 4: 0 = the round-1 kernels (k_prep + k_chain) for every stream
 	// random time factors beyond 2x stretch (:639-640): engine state per stream (lives as long as the handle, like the
@@ -173,6 +175,15 @@ static Ctx make_ctx(b200s_engine *e) {
 	x.rot = e->dRot; x.twiddle = e->dTwiddle; x.pretw = e->dPretw; x.anaTab = e->dAnaTab;
 	x.rot0 = e->rot0; x.rotStep = e->rotStep;
 	x.one = 1.0f;
+	{
+		static int env = -2;
+		if (env == -2) {
+			const char *v = getenv("B200S_L2PF");
+			env = v ? atoi(v) : -1;
+		}
+		const int want = e->l2pf >= 0 ? e->l2pf : env >= 0 ? env : B200S_L2PF_DEFAULT;
+		x.l2pf = (want >= 8 && (want & (want - 1)) == 0) ? want : 0;
+	}
 	x.sched = e->dSched;
 	x.histCur = e->dHist[e->histCur]; x.histNext = e->dHist[e->histCur ^ 1];
 	x.pend = e->dPend; x.pendWp = e->dPendWp;
@@ -871,15 +882,13 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 					ChainKernel kc = chain2_kernel(g, g.C == 1 && !e->exactMath);
 					int _rc;
 					if ((_rc = prof_mark(e, PK_CHAIN, true))) return _rc;
-					if (g.C == 1 && x.sCount >= 2 && (e->dual < 0 ? dual_enabled() : e->dual != 0)) { // pairs of mono streams that share their schedule: the packed wavefront
+					if (g.C == 1 && (e->dual < 0 ? dual_enabled() : e->dual != 0)) { // mono: two streams per warp on the packed wavefront
 						ChainKernel kd = e->exactMath ? chain6_kernel<false, true>(g.L) : chain6_kernel<true, true>(g.L);
-						B200S_LAUNCH(kd, dim3(x.sCount / 2), dim3(32), smem_chain6(), st, x);
-						CKL();
-						x.dualRan = 1; // k_chain_direct2 below: the pairs that do not, and the odd stream (every other CTA exits at once)
+						B200S_LAUNCH(kd, dim3((x.sCount + 1) / 2), dim3(32), smem_chain6(), st, x);
+					} else {
+						B200S_LAUNCH(kc, dim3(x.sCount), dim3(32 * W), smem_chain2(g.C, W), st, x);
 					}
-					B200S_LAUNCH(kc, dim3(x.sCount), dim3(32 * W), smem_chain2(g.C, W), st, x);
 					CKL();
-					x.dualRan = 0;
 					if ((_rc = prof_mark(e, PK_CHAIN, false))) return _rc;
 				} else {
 					dim3 grid((x.sCount + kChainWarps - 1) / kChainWarps), block(32 * kChainWarps);
@@ -1148,6 +1157,7 @@ int b200s_set_tuning(b200s_engine *e, int key, int value) {
 	else if (key == 3 && (value == 0 || value == 1)) e->exactMath = value;
 	else if (key == 4 && (value == 0 || value == 1)) e->stepMajor = value;
 	else if (key == 5 && (value == 0 || value == 1)) e->dual = value;
+	else if (key == 6 && (value == 0 || value == 8 || value == 16 || value == 32 || value == 64 || value == 128)) e->l2pf = value;
 	else {
 		e->err = "b200s_set_tuning: unknown key or value";
 		return B200S_EINVAL;
