@@ -369,12 +369,15 @@ static ChainKernel chain6_kernel(int L) {
 	default: return k_chain_direct6<8, FAST, DUAL>;
 	}
 }
-// mono plain path: pairs of streams on the packed wavefront (k_chain_direct6<.., DUAL>) before k_chain_direct2; B200S_DUAL=0 switches it off (A/B)
+// mono plain path: pairs of streams on the packed wavefront (k_chain_direct6<.., DUAL>) instead of k_chain_direct2.  Off by
+// default: measured on B200 (profiles/r03_chain6_ab.md) it is no faster (4.99 vs 4.85 ms for 4096 streams) although it issues
+// 40 % fewer instructions per stream -- the wavefront kernels are bound by dependent latency at 7 warps per SM, not by issue.
+// B200S_DUAL=1 / b200s_set_tuning(e, 5, 1) switch it on (cross-check in the tests).
 static bool dual_enabled() {
 	static int env = -1;
 	if (env < 0) {
 		const char *v = getenv("B200S_DUAL");
-		env = v ? (atoi(v) != 0) : 1;
+		env = v ? (atoi(v) != 0) : 0;
 	}
 	return env != 0;
 }
@@ -614,7 +617,9 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	CK(cudaFuncSetAttribute(synth_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_synth(g)));
 	CK(cudaFuncSetAttribute(k_flush_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * g.B)));
 	CK(cudaFuncSetAttribute(chain_kernel(g, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, false, true)));
+#ifdef B200S_KEEP_OLD_KERNELS // (without the old generations chain_kernel(g, true) is the same function: do not shrink its limit again)
 	CK(cudaFuncSetAttribute(chain_kernel(g, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain(g, true)));
+#endif
 	CK(cudaFuncSetAttribute(chain2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain2(g.C, CH2_MAXW)));
 	CK(cudaFuncSetAttribute(chain2_kernel(g, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain2(g.C, CH2_MAXW)));
 #ifdef B200S_KEEP_OLD_KERNELS

@@ -61,13 +61,15 @@ def test_product_sources_never_touch_the_oracle():
 
 
 # ------------------------------------------------------------------ kernels under the emulator
-def _emu(path, batch, exact_math=True, gen=0):
+def _emu(path, batch, exact_math=True, gen=0, pairs=False):
     from signalsmith_stretch_b200 import BatchStretch
 
     e = BatchStretch(batch, lib_path=path)
     e.set_tuning(3, 1 if exact_math else 0)  # the bit-exact checks run the phase chain in the reference's own arithmetic
     if gen:
         e.set_tuning(0, gen)  # generation of the stereo direct chain kernel (0 = the default)
+    if pairs:
+        e.set_tuning(5, 1)  # mono plain path: two streams per warp on the packed wavefront (k_chain_direct6<.., DUAL>)
     return e
 
 
@@ -446,8 +448,8 @@ def test_stereo_chain_generation6_with_diverging_streams_and_silence(emu_libs, o
 
 
 MONO_PAIRS = [
-    # mono plain calls: pairs of streams run on the packed wavefront (k_chain_direct6<.., DUAL>), the odd stream of the
-    # batch and pairs whose schedules differ on k_chain_direct2.  (block, interval) -> long vertical step L = 1 .. 8
+    # mono plain calls with two streams per warp on the packed wavefront (k_chain_direct6<.., DUAL>, tuning key 5); the odd
+    # stream of the batch and pairs whose schedules differ run alone through the same kernel.  (block, interval) -> L = 1 .. 8
     ("L1", 256, 256, 0.8), ("L2", 512, 256, 1.25), ("L3", 384, 128, 0.8), ("L4", 512, 128, 0.5), ("L5", 500, 100, 1.6), ("L8", 512, 64, 0.8),
 ]
 
@@ -457,7 +459,7 @@ def test_mono_stream_pairs_on_the_packed_chain_bit_exact_vs_oracle(emu_libs, ora
     S = 5  # two pairs and an odd stream
     x = signals.batch("harmonic", S, 1, 12 * B, 48000)
     x[3, :, 3 * B:7 * B] = 0.0  # stream 3 falls silent for a while: the pair (2, 3) stops sharing its schedule
-    g = _emu(emu_libs["exact"], S)
+    g = _emu(emu_libs["exact"], S, pairs=True)
     g.configure(1, B, H)
     chunk = 40 * H + 17  # more than 32 blocks per call: a second group of lanes
     y = signals.run_batch(g, x, ratio, chunk)
@@ -469,7 +471,7 @@ def test_mono_stream_pairs_on_the_packed_chain_bit_exact_vs_oracle(emu_libs, ora
 def test_mono_stream_pairs_at_preset_size_bit_exact_vs_oracle(emu_libs, oracle_port):
     for cfg, ratio, n, chunk in ((lambda o: o.presetDefault(1, 48000.0), 0.8, 2 * 57600, 46080), (lambda o: o.presetCheaper(1, 48000.0), 2.0, 30000, 20000)):
         x = signals.batch("harmonic", 2, 1, n, 48000)
-        g = _emu(emu_libs["exact"], 2)
+        g = _emu(emu_libs["exact"], 2, pairs=True)
         cfg(g)
         y = signals.run_batch(g, x, ratio, chunk)
         ref = _oracle_batch(oracle_port, cfg, x, ratio, chunk)
@@ -480,7 +482,7 @@ def test_fast_chain_arithmetic_of_generation6_and_of_mono_pairs_stays_within_tol
     cases = [(PRESET_CALLS[3], 6), (PRESET_CALLS[4], 6), (("default_mono_0.8x", lambda o: o.presetDefault(1, 48000.0), 1, 0.8, 2 * 57600, 46080), 0)]
     for (name, cfg, C, ratio, n, chunk), gen in cases:
         x = signals.batch("harmonic", 2, C, n, 48000)
-        g = _emu(emu_libs["exact"], 2, exact_math=False, gen=gen)
+        g = _emu(emu_libs["exact"], 2, exact_math=False, gen=gen, pairs=(C == 1))
         cfg(g)
         y = signals.run_batch(g, x, ratio, chunk)
         ref = _oracle_batch(oracle_port, cfg, x, ratio, chunk)
