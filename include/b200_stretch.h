@@ -59,8 +59,7 @@ int b200s_set_sub_batches(b200s_engine *e, int n);
  *   key 0 values: 1..6 (4 = k_chain_direct4, 5 = warp-specialised, 6 = k_chain_direct6)
  *   key 4: mapped / formant calls on the step-major path (1, default) or on the round-1 kernels (0)
  *   key 5: mono plain calls: two streams per warp on the packed wavefront k_chain_direct6 (1) or every stream on its own
- *          warp(s), k_chain_direct2 (0, default: measured equally fast)
- *   key 6: k_chain_direct6 only: bins per bulk L2 prefetch of a spectrum row (0 = off, default: measured slower with it) */
+ *          warp(s), k_chain_direct2 (0, default: measured equally fast) */
 int b200s_set_tuning(b200s_engine *e, int key, int value);
 
 /* ---- configuration: presetDefault / presetCheaper / configure / reset  (:49-94) ---- */

@@ -60,6 +60,8 @@ def build_library(verbose=False):
            "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-o", out, src]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    if os.environ.get("B200S_EXTRA_NVCC"):  # profiling builds (e.g. -DB200S_CHAIN_PROBES); never set for the shipped library
+        cmd[1:1] = os.environ["B200S_EXTRA_NVCC"].split()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise StretchError("nvcc failed:\n" + r.stdout + r.stderr)

@@ -52,28 +52,18 @@ __device__ __forceinline__ f2 ld_f2s(const float2 *p) {
 	return f2_make(v.x, v.y);
 }
 // Prediction::makeOutput (:596-603) where Prediction::energy is |input|^2 (plain path): the weak branch's norm is energy + noiseFloor
+template <int PROBE = 0>
 __device__ __forceinline__ float2 make_output_fast_e(float2 phase, float energy, float2 input) {
 	const float pn = ffma(phase.x, phase.x, phase.y * phase.y);
 	const bool weak = pn <= B200S_NOISE_FLOOR;
-	const float g = sqrt_fast(energy) * rsqrt_fast(weak ? energy + B200S_NOISE_FLOOR : pn);
+	const float g = PROBE == 1 ? ffma(energy, 0.5f, weak ? energy + B200S_NOISE_FLOOR : pn) : sqrt_fast(energy) * rsqrt_fast(weak ? energy + B200S_NOISE_FLOOR : pn);
 	return make_float2((weak ? input.x : phase.x) * g, (weak ? input.y : phase.y) * g);
 }
 
-// Ask L2 for `bytes` (a multiple of 16) at a 16-byte aligned global address: ONE request for a long contiguous piece of a
-// spectrum row.  The chain's own accesses are 128-byte (stereo) / 64-byte (mono) pieces of 32+ different rows per warp and
-// chunk; measured (round 3: the kernel's time follows its bytes, not its instructions -- generation 6 with 11 % fewer
-// instructions ran no faster, two mono streams per warp no faster than one) that scattered pattern, not issue or latency,
-// bounds the chain beyond ~500 streams.  The chunk fills then hit L2.
-__device__ __forceinline__ void l2_prefetch_bulk(const void *p, unsigned bytes) {
-#ifndef B200S_EMU
-	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-#else
-	(void)p;
-	(void)bytes;
-#endif
-}
-
-template <int LT, bool FAST, bool DUAL>
+// PROBE (profiling builds only, results are WRONG): ablations that time what a part of the step costs --
+//   1: no SFU (rcp / rsqrt / sqrt replaced by one FMA)   2: the locked channel copies the leader (no second makeOutput)
+//   3: no interpolation loads (the twists use the prelim bin's input)   4: no lane-to-lane hand-off (every lane re-reads its own slots)
+template <int LT, bool FAST, bool DUAL, int PROBE = 0>
 __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 	const Cfg &g = x.cfg;
 	const int K = g.K;
@@ -112,47 +102,52 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 		const float longTf = fmul((float)LT, tf);
 		const bool farAny = __any_sync(0xffffffffu, active && longTf > (float)CH6_FAR);
 		// lane 0's predecessor block: the state rows (first group of the call) or the last block of the previous group.
-		// half h = channel h (stereo) or stream s + h (DUAL); rows are planar float2
-		const float2 *prevOut[2];
-		const float *prevE[2];
-#pragma unroll
-		for (int h = 0; h < 2; ++h) {
-			if constexpr (DUAL) {
-				prevOut[h] = base == 0 ? x.stOut + (size_t)sH[h] * K : x.Y + coef_off(x, sH[h], base - 1, 0);
-				prevE[h] = x.stPredE + (size_t)sH[h] * K; // base == 0 only; later groups recompute it, see the fill
-			} else {
-				prevOut[h] = base == 0 ? x.stOut + ((size_t)s * 2 + h) * K : x.Y + coef_off(x, s, base - 1, h);
-				prevE[h] = x.stPredE + ((size_t)s * 2 + h) * K;
-			}
+		// half h = channel h (stereo) or stream sH[h] (DUAL); rows are planar float2.  Pointer of half 0 + distance to half 1
+		// (not arrays: indexed by a run-time half they would live in local memory)
+		const float2 *prevOut0;
+		const float *prevE0; // base == 0 only; later groups recompute the energy from the predecessor's input row, see the fill
+		ptrdiff_t prevOutD, prevED;
+		if constexpr (DUAL) {
+			prevOut0 = base == 0 ? x.stOut + (size_t)sH[0] * K : x.Y + coef_off(x, sH[0], base - 1, 0);
+			prevOutD = (base == 0 ? x.stOut + (size_t)sH[1] * K : x.Y + coef_off(x, sH[1], base - 1, 0)) - prevOut0;
+			prevE0 = x.stPredE + (size_t)sH[0] * K;
+			prevED = (ptrdiff_t)(sH[1] - sH[0]) * K;
+		} else {
+			prevOut0 = base == 0 ? x.stOut + (size_t)s * 2 * K : x.Y + coef_off(x, s, base - 1, 0);
+			prevOutD = K; // the channel rows of a block are adjacent (state rows and Y rows alike)
+			prevE0 = x.stPredE + (size_t)s * 2 * K;
+			prevED = K;
 		}
 		// Prediction::energy of a block on this path is |input|^2 of its own spectrum (:679,:708): the chain never stores
 		// it -- the next group recomputes it from the predecessor's input row, k_commit from the final input spectrum
 		// (DUAL: k_commit of the mono path reads the last block's row of cE, written below)
 		const int prevSlotIn = base == 0 ? 0 : x.frames[(size_t)s * x.maxFrames + base - 1].inSlot;
 		const float4 *prevInIl = nullptr, *myInIl = nullptr;
-		const float2 *prevInD[2] = {nullptr, nullptr}, *myInD[2] = {nullptr, nullptr}, *myPvD[2] = {nullptr, nullptr};
-		const float4 *myPvIl = nullptr;
-		float2 *yBaseD[2] = {nullptr, nullptr};
+		const float2 *prevInD0 = nullptr, *myInD[2] = {nullptr, nullptr};
+		ptrdiff_t prevInDD = 0;
+		float2 *ylA = nullptr, *ylB = nullptr; // Band::output rows of this lane's block: the two halves (channels, or streams A / B)
 		float *eRowD[2] = {nullptr, nullptr};
-		float2 *yBase = nullptr;
 		if constexpr (DUAL) {
+			if (base > 0) {
+				prevInD0 = spec_slot(x, sH[0], prevSlotIn, 0);
+				prevInDD = spec_slot(x, sH[1], prevSlotIn, 0) - prevInD0;
+			}
 #pragma unroll
 			for (int h = 0; h < 2; ++h) {
-				prevInD[h] = base == 0 ? nullptr : spec_slot(x, sH[h], prevSlotIn, 0);
 				myInD[h] = spec_slot(x, sH[h], fr.inSlot, 0);
 				U.rowIn[h][lane] = myInD[h];
-				myPvD[h] = spec_slot(x, sH[h], fr.prevSlot, 0);
-				U.rowPv[h][lane] = myPvD[h];
-				yBaseD[h] = x.Y + coef_off(x, sH[h], base, 0); // Band::output row of block base + r of stream h: yBaseD[h] + r * K
+				U.rowPv[h][lane] = spec_slot(x, sH[h], fr.prevSlot, 0);
 				eRowD[h] = x.cE + coef_off(x, sH[h], active ? f : base, 0);
 			}
+			ylA = x.Y + coef_off(x, sH[0], active ? f : base, 0);
+			ylB = x.Y + coef_off(x, sH[1], active ? f : base, 0);
 		} else {
 			prevInIl = base == 0 ? nullptr : il_row(x, s, prevSlotIn);
 			myInIl = il_row(x, s, fr.inSlot);
 			U.rowIn[0][lane] = myInIl;
-			myPvIl = il_row(x, s, fr.prevSlot);
-			U.rowPv[0][lane] = myPvIl;
-			yBase = x.Y + coef_off(x, s, base, 0); // Band::output row of block base + r, channel c: yBase + (2r + c) * K
+			U.rowPv[0][lane] = il_row(x, s, fr.prevSlot);
+			ylA = x.Y + coef_off(x, s, active ? f : base, 0);
+			ylB = ylA + K;
 		}
 		const bool lastFrame = DUAL && active && f == cl.nFrames - 1; // its Prediction::energy is the state the next call continues from
 		__syncwarp();
@@ -190,23 +185,10 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 		// The ring slots it writes (the 8 bins after the chunk's own 8, per lane) are disjoint from what the chunk in
 		// progress reads (at most CH6_FAR + 3 bins behind its own 8: 8 + 8 + CH6_FAR + 3 <= CH3_RING).
 		// Lane 0's predecessor: finals of bins kf+1 .. kf+8 into the padding slots before rows [buf][0..7] of pvy (step i
-		// reads, for step i+1, the slot before its own row), energies of bins kf .. kf+7 into the padding before rows
-		// [bin & 15] of eR.  None of these slots is read by the chunk in progress (other buffer / other half of the ring).
+		// reads, for step i+1, the slot before its own row), energies of the same bins into the padding before rows
+		// [bin & 15] of eR (every step reads the energy of the NEXT step's bin).  None of these slots is read by the chunk in
+		// progress (other buffer / other half of the ring).
 		auto fill = [&](int kf, int buf) {
-			if (x.l2pf > 0 && (kf & (x.l2pf - 1)) == 0) { // every l2pf bins (a power of two >= 8): this lane's own rows, the l2pf bins after those staged next
-				const int q0 = max(kf + x.l2pf - G * lane, 0), q1 = min(kf + 2 * x.l2pf - G * lane, K);
-				if (active && q1 > q0) {
-					if constexpr (DUAL) {
-						for (int h = 0; h < (pairOk ? 2 : 1); ++h) {
-							l2_prefetch_bulk(myInD[h] + q0, 8u * (unsigned)(q1 - q0));
-							l2_prefetch_bulk(myPvD[h] + q0, 8u * (unsigned)(q1 - q0));
-						}
-					} else {
-						l2_prefetch_bulk(myInIl + q0, 16u * (unsigned)(q1 - q0));
-						l2_prefetch_bulk(myPvIl + q0, 16u * (unsigned)(q1 - q0));
-					}
-				}
-			}
 			if constexpr (DUAL) {
 				const float2 *rIn[2][8], *rPv[2][8];
 #pragma unroll
@@ -255,16 +237,16 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 			{ // lane 0's predecessor finals: 4 floats per bin, one 4-byte copy per lane
 				const int i = lane >> 2, comp = lane & 3, qq = kf + 1 + i;
 				const int h = comp & 1, part = comp >> 1; // tile slot component {re0, re1, im0, im1} -> (half, re / im)
-				if (qq < K) cp_async4((float *)(&U.pvy[buf][i][0] - 1) + comp, (const float *)((h ? prevOut[1] : prevOut[0]) + qq) + part);
+				if (qq < K) cp_async4((float *)(&U.pvy[buf][i][0] - 1) + comp, (const float *)(prevOut0 + h * prevOutD + qq) + part);
 			}
-			if (lane < 2 * CHAIN_CH) { // ... and its Prediction::energy {half 0, half 1}
-				const int qq = kf + (lane >> 1), h = lane & 1;
+			if (lane < 2 * CHAIN_CH) { // ... and its Prediction::energy {half 0, half 1}, bins kf+1 .. kf+8 (read one step ahead, too)
+				const int qq = kf + 1 + (lane >> 1), h = lane & 1;
 				float *pad = (float *)(&U.eR[qq & (CH6_ER - 1)][0] - 1) + h;
 				if (qq < K) {
 					if (base == 0) {
-						cp_async4(pad, (h ? prevE[1] : prevE[0]) + qq);
+						cp_async4(pad, prevE0 + h * prevED + qq);
 					} else if constexpr (DUAL) {
-						*pad = xnorm((h ? prevInD[1] : prevInD[0])[qq]);
+						*pad = xnorm((prevInD0 + h * prevInDD)[qq]);
 					} else {
 						const float4 v = prevInIl[qq];
 						*pad = h ? xnorm(make_float2(v.y, v.w)) : xnorm(make_float2(v.x, v.z));
@@ -276,10 +258,65 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 		// final output of the previous block at the prelim bin of the NEXT step (read from the tile at the end of each step);
 		// for the first step: lane 0's predecessor at bin 0, nothing for the others (their q is negative)
 		c2 roN = zc;
+		f2 cRe = z2; // ... and its Prediction::energy at that bin
 		if (lane == 0) {
-			const float2 a = prevOut[0][0], bb = prevOut[1][0];
+			const float2 a = prevOut0[0], bb = prevOut0[prevOutD];
 			roN = c2{f2_make(a.x, bb.x), f2_make(a.y, bb.y)};
+			if (base == 0) {
+				cRe = f2_make(prevE0[0], prevE0[prevED]);
+			} else if constexpr (DUAL) {
+				cRe = f2_make(xnorm(prevInD0[0]), xnorm(prevInD0[prevInDD]));
+			} else {
+				const float4 v = prevInIl[0];
+				cRe = f2_make(xnorm(make_float2(v.x, v.z)), xnorm(make_float2(v.y, v.w)));
+			}
 		}
+		// Everything a step reads from BEHIND its prelim bin -- the interpolation points of the two twists, Prediction::input of
+		// the final bin, the predecessor's energy -- is loaded ONE STEP AHEAD into these registers, so that the shared-memory
+		// latency (and the float -> int conversions in front of the addresses) overlaps the previous step's arithmetic instead
+		// of stalling this one (ncu, round 3: 10 % of the kernel's stall samples sat on the consumers of these loads).
+		c2 cLo2 = zc, cHi2 = zc, cLo1 = zc, cHi1 = zc, cInB = zc;
+		float cF2s = 0.f, cF1s = 0.f;
+		auto preload = [&](const int qn, auto farTag, auto intTag, bool withRe) {
+			constexpr bool FAR = decltype(farTag)::value, INTERIOR = decltype(intTag)::value;
+			const int bn = qn - LT - 1, p2 = qn - 1, p1 = qn - D1;
+			// the long twist of bin p2 needs input interpolated at p2 - L*tf, the short twist of bin p1 at p1 - tf  (:750,:757)
+			const float pf2 = (float)p2;
+			const float pf1 = D1 == 1 ? pf2 : (float)p1;
+			const float i2 = fsub(pf2, longTf);
+			const int l2 = (int)floorf(i2);
+			cF2s = fsub(i2, (float)l2);
+			const float i1 = fsub(pf1, tf);
+			const int l1 = (int)floorf(i1);
+			cF1s = fsub(i1, (float)l1);
+			if (withRe) cRe = ld_f2s(&U.eR[qn & (CH6_ER - 1)][0] + lane - (PROBE == 4 ? 0 : 1));
+			cInB = sel_c2(INTERIOR || (active && (unsigned)bn < (unsigned)K), ld_t<DUAL>(&U.in[bn & (CH3_RING - 1)][lane])); // Prediction::input at bin bn
+			if constexpr (PROBE == 3) {
+				cLo2 = cHi2 = cLo1 = cHi1 = cInB;
+			} else if constexpr (!FAR) {
+				cLo2 = sel_c2(INTERIOR || l2 >= 0, ld_t<DUAL>(&U.in[l2 & (CH3_RING - 1)][lane]));
+				cHi2 = sel_c2(INTERIOR || l2 >= -1, ld_t<DUAL>(&U.in[(l2 + 1) & (CH3_RING - 1)][lane]));
+				cLo1 = sel_c2(INTERIOR || l1 >= 0, ld_t<DUAL>(&U.in[l1 & (CH3_RING - 1)][lane]));
+				cHi1 = sel_c2(INTERIOR || l1 >= -1, ld_t<DUAL>(&U.in[(l1 + 1) & (CH3_RING - 1)][lane]));
+			} else { // extreme stretch (> 2x): gather straight from the spectrum row(s)
+				auto gather = [&](int bb) -> c2 {
+					if (bb < 0 || bb >= K) return zc;
+					if constexpr (DUAL) {
+						const float2 a = myInD[0][bb], c = myInD[1][bb];
+						return c2{f2_make(a.x, c.x), f2_make(a.y, c.y)};
+					} else {
+						return ld_c2s(myInIl + bb);
+					}
+				};
+				cLo2 = gather(l2);
+				cHi2 = gather(l2 + 1);
+				cLo1 = gather(l1);
+				cHi1 = gather(l1 + 1);
+			}
+		};
+		// first step (every q <= 0: nothing behind it is inside the spectrum, but the masks need their indices)
+		if (farAny) preload(-G * lane, std::true_type{}, std::false_type{}, false);
+		else preload(-G * lane, std::false_type{}, std::false_type{}, false);
 		int cb = 0; // buffer of the chunk being computed
 		for (int k0 = 0; k0 < steps; k0 += CHAIN_CH, cb ^= 1) {
 			cp_async_wait_all(); // this chunk's tiles (issued one chunk ago)
@@ -288,50 +325,22 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 			// ---------------- CHAIN_CH steps ----------------
 			// INTERIOR: every lane's q, b and interpolation points are inside [0, K) for the whole chunk, so all the
 			// edge masks below are identities and are compiled out (about nine chunks in ten)
-			auto step = [&](const int i, auto farTag, auto intTag) {
-				constexpr bool FAR = decltype(farTag)::value, INTERIOR = decltype(intTag)::value;
+			auto step = [&](const int i, const int u, float2 *const sA, float2 *const sB, auto farTag, auto intTag, auto actTag) {
+				constexpr bool FAR = decltype(farTag)::value, INTERIOR = decltype(intTag)::value, ALLACT = decltype(actTag)::value;
 				const int q = k0 + i - G * lane;
 				const int b = q - LT - 1, p2 = q - 1, p1 = q - D1;
 				const bool qIn = INTERIOR || (active && (unsigned)q < (unsigned)K);
 				const bool p2In = INTERIOR || (active && (unsigned)p2 < (unsigned)K);
 				const bool p1In = INTERIOR || (active && (unsigned)p1 < (unsigned)K);
-				const bool bIn = INTERIOR || (active && (unsigned)b < (unsigned)K);
-				// the long twist of bin p2 needs input interpolated at p2 - L*tf, the short twist of bin p1 at p1 - tf  (:750,:757)
-				const float pf2 = (float)p2;
-				const float pf1 = D1 == 1 ? pf2 : (float)p1;
-				const float i2 = fsub(pf2, longTf);
-				const int l2 = (int)floorf(i2);
-				const float f2s = fsub(i2, (float)l2);
-				const float i1 = fsub(pf1, tf);
-				const int l1 = (int)floorf(i1);
-				const float f1s = fsub(i1, (float)l1);
-				// previous block's final output / energy at bin q
+				// loaded one step ahead: interpolation points / fractions of the twists of bins p2 and p1, Prediction::input at bin b,
+				// the previous block's final output / energy at bin q
+				const c2 lo2 = cLo2, hi2 = cHi2, lo1 = cLo1, hi1 = cHi1, inB = cInB;
+				const float f2s = cF2s, f1s = cF1s;
+				const f2 re = cRe;
 				c2 ro = roN;
-				const f2 re = ld_f2s(&U.eR[q & (CH6_ER - 1)][0] + lane - 1);
 				const c2 inq = ld_t<DUAL>(&U.in[q & (CH3_RING - 1)][lane]);
 				c2 pv = ld_t<DUAL>(&U.pvy[cb][i][lane]);
-				const c2 inB = sel_c2(bIn, ld_t<DUAL>(&U.in[b & (CH3_RING - 1)][lane])); // Prediction::input at bin b
-				c2 lo2, hi2, lo1, hi1;
-				if constexpr (!FAR) {
-					lo2 = sel_c2(INTERIOR || l2 >= 0, ld_t<DUAL>(&U.in[l2 & (CH3_RING - 1)][lane]));
-					hi2 = sel_c2(INTERIOR || l2 >= -1, ld_t<DUAL>(&U.in[(l2 + 1) & (CH3_RING - 1)][lane]));
-					lo1 = sel_c2(INTERIOR || l1 >= 0, ld_t<DUAL>(&U.in[l1 & (CH3_RING - 1)][lane]));
-					hi1 = sel_c2(INTERIOR || l1 >= -1, ld_t<DUAL>(&U.in[(l1 + 1) & (CH3_RING - 1)][lane]));
-				} else { // extreme stretch (> 2x): gather straight from the spectrum row(s)
-					auto gather = [&](int bb) -> c2 {
-						if (bb < 0 || bb >= K) return zc;
-						if constexpr (DUAL) {
-							const float2 a = myInD[0][bb], c = myInD[1][bb];
-							return c2{f2_make(a.x, c.x), f2_make(a.y, c.y)};
-						} else {
-							return ld_c2s(myInIl + bb);
-						}
-					};
-					lo2 = gather(l2);
-					hi2 = gather(l2 + 1);
-					lo1 = gather(l1);
-					hi1 = gather(l1 + 1);
-				}
+				preload(q + 1, farTag, intTag, true); // ... and the same for the next step
 				const c2 in1 = D1 == 1 ? inP : inP2; // Prediction::input at bin p1
 				c2 newPre, T2, t1n;
 				f2 newE, eB;
@@ -341,7 +350,7 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 					const f2 e = fnorm2(inq);                    // :679 (identity map: energy = |input|^2)
 					const c2 ph0 = fmul_c(ro, fmulc_c(inq, pv)); // :714-715
 					const f2 den = f2_make(fmaxf(f2_lo(re), f2_lo(e)), fmaxf(f2_hi(re), f2_hi(e))) + f2_make(B200S_NOISE_FLOOR, B200S_NOISE_FLOOR);
-					const f2 rden = f2_make(rcp_fast(f2_lo(den)), rcp_fast(f2_hi(den)));
+					const f2 rden = PROBE == 1 ? fma2(den, f2_make(0.5f, 0.5f), den) : f2_make(rcp_fast(f2_lo(den)), rcp_fast(f2_hi(den)));
 					newPre = sel_c2(qIn, c2{mul2(ph0.re, rden), mul2(ph0.im, rden)}); // :716
 					newE = sel_f2(qIn, e);
 					T2 = sel_c2(p2In, fmulc_c(inP, flerp2(lo2, hi2, f2s)));  // long twist at p2 (:758)
@@ -398,17 +407,17 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 						if constexpr (A == 1) RF[1] = RF[1] + sel_c2(b + 1 < K - 1, fmulc_c(preA, t1A));
 					}
 					if constexpr (DUAL) { // :788, each half its own (mono) stream
-						const float2 oA = make_output_fast_e(pick(false, ph2), f2_lo(eB), pick(false, inB));
-						const float2 oB = make_output_fast_e(pick(true, ph2), f2_hi(eB), pick(true, inB));
+						const float2 oA = make_output_fast_e<PROBE>(pick(false, ph2), f2_lo(eB), pick(false, inB));
+						const float2 oB = make_output_fast_e<PROBE>(pick(true, ph2), f2_hi(eB), pick(true, inB));
 						oc = c2{f2_make(oA.x, oB.x), f2_make(oA.y, oB.y)};
 					} else { // the louder channel (first on ties, :733) leads, the other is locked in phase (:791-799)
 						const bool m = f2_hi(eB) > f2_lo(eB);
 						const float maxE = m ? f2_hi(eB) : f2_lo(eB);
 						const float2 phase = pick(m, ph2), pinM = pick(m, inB);
-						const float2 outM = make_output_fast_e(phase, maxE, pinM); // :788
+						const float2 outM = make_output_fast_e<PROBE>(phase, maxE, pinM); // :788
 						const float2 inO = pick(!m, inB);
 						const float eO = m ? f2_lo(eB) : f2_hi(eB);
-						const float2 outO = make_output_fast_e(fmul_f(outM, fmulc_f(inO, pinM)), eO, inO);
+						const float2 outO = PROBE == 2 ? outM : make_output_fast_e<PROBE>(fmul_f(outM, fmulc_f(inO, pinM)), eO, inO);
 						oc = c2{f2_make(m ? outO.x : outM.x, m ? outM.x : outO.x), f2_make(m ? outO.y : outM.y, m ? outM.y : outO.y)};
 					}
 				} else {
@@ -447,50 +456,41 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 #pragma unroll
 				for (int u = 0; u + 1 < LT; ++u) RF[u] = RF[u + 1];
 				RF[LT - 1] = rNew;
-				U.pvy[cb][i][lane] = pack_t<DUAL>(oc);
-				if constexpr (DUAL) {
-					if (lastFrame && (unsigned)b < (unsigned)K) {
-						eRowD[0][b] = f2_lo(eB);
-						eRowD[1][b] = f2_hi(eB);
-					}
-				}
-				__syncwarp();
-				roN = ld_t<DUAL>(&U.pvy[cb][i][0] + lane - 1); // the next step's prelim bin of this lane is the bin lane-1 just finalised
-			};
-			// unrolled by 4 (for L = 4 the register FIFOs rotate by pure renaming) so that the hot loop stays in the
-			// instruction cache; branch-free inside
-			auto run_chunk = [&](auto farTag, auto intTag) {
-#pragma unroll 1
-				for (int h = 0; h < CHAIN_CH; h += 4) {
-#pragma unroll
-					for (int u = 0; u < 4; ++u) step(h + u, farTag, intTag);
-				}
-			};
-			if (farAny) run_chunk(std::true_type{}, std::false_type{});
-			else if (k0 >= interiorFrom && k0 + CHAIN_CH <= K) run_chunk(std::false_type{}, std::true_type{});
-			else run_chunk(std::false_type{}, std::false_type{});
-			// ---------------- write the chunk's finals back: planar Band::output rows, 32 B per row and quarter-warp;
-			//                  all tile reads first, then the stores (row addresses are arithmetic) ----------------
-			{
-				float4 v[8];
-#pragma unroll
-				for (int it = 0; it < 8; ++it) v[it] = U.pvy[cb][fillI][fillF + 4 * it];
-#pragma unroll
-				for (int it = 0; it < 8; ++it) {
-					const int fl = fillF + 4 * it;
-					const int b = k0 + fillI - G * fl - LT - 1;
-					if (fl < nAct && (unsigned)b < (unsigned)K) {
-						if constexpr (DUAL) {
-							yBaseD[0][(size_t)fl * K + b] = make_float2(v[it].x, v[it].z);
-							yBaseD[1][(size_t)fl * K + b] = make_float2(v[it].y, v[it].w);
-						} else {
-							float2 *row = yBase + (size_t)(2 * fl) * K + b;
-							row[0] = make_float2(v[it].x, v[it].z);
-							row[K] = make_float2(v[it].y, v[it].w);
+				U.pvy[cb][i][lane] = pack_t<DUAL>(oc); // for the next lane (its prelim bin of the next step)
+				// Band::output of bin b goes straight to its rows, 8 bytes per half and step: L2 merges the four steps of a
+				// sector long before it is evicted, and the separate write-back pass at the end of every chunk (tile reads,
+				// address arithmetic, predicated stores: 14 % of the kernel's stall samples, ncu round 3) is gone
+				// (sA / sB: the slots of the final bins of the four unrolled steps, so the addresses are one base + immediates;
+				//  ALLACT: every lane of the warp owns a block, the common case -- nothing to guard in an interior chunk)
+				if ((ALLACT && INTERIOR) || (active && (INTERIOR || (unsigned)b < (unsigned)K))) {
+					sA[u] = make_float2(f2_lo(oc.re), f2_lo(oc.im));
+					sB[u] = make_float2(f2_hi(oc.re), f2_hi(oc.im));
+					if constexpr (DUAL) {
+						if (lastFrame) {
+							eRowD[0][b] = f2_lo(eB);
+							eRowD[1][b] = f2_hi(eB);
 						}
 					}
 				}
-			}
+				__syncwarp();
+				roN = ld_t<DUAL>(&U.pvy[cb][i][0] + lane - (PROBE == 4 ? 0 : 1)); // the next step's prelim bin of this lane is the bin lane-1 just finalised
+			};
+			// unrolled by 4 (for L = 4 the register FIFOs rotate by pure renaming) so that the hot loop stays in the
+			// instruction cache; branch-free inside
+			auto run_chunk = [&](auto farTag, auto intTag, auto actTag) {
+				float2 *const cA = ylA + (k0 - G * lane - LT - 1), *const cB = ylB + (k0 - G * lane - LT - 1); // slot of step 0's final bin
+#pragma unroll 1
+				for (int h = 0; h < CHAIN_CH; h += 4) {
+					float2 *const sA = cA + h, *const sB = cB + h;
+#pragma unroll
+					for (int u = 0; u < 4; ++u) step(h + u, u, sA, sB, farTag, intTag, actTag);
+				}
+			};
+			if (farAny) run_chunk(std::true_type{}, std::false_type{}, std::false_type{});
+			else if (k0 >= interiorFrom && k0 + CHAIN_CH <= K) {
+				if (nAct == 32) run_chunk(std::false_type{}, std::true_type{}, std::true_type{});
+				else run_chunk(std::false_type{}, std::true_type{}, std::false_type{});
+			} else run_chunk(std::false_type{}, std::false_type{}, std::false_type{});
 			__syncwarp();
 		}
 	}

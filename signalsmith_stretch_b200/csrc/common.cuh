@@ -120,7 +120,6 @@ struct Ctx {
 	// stIl [S][2][K] holds such copies of stIn / stPrev, made by k_plan at the start of the call
 	float4 *stIl;
 	int specIl;
-	int l2pf;    // k_chain_direct6: bulk L2 prefetch of the spectrum rows ahead of the chunk fills (b200s_set_tuning key 6)
 	int wsRan; // k_chain_ws ran before k_chain_direct4 in this call: the latter only takes the streams the former left (chain_ws.cuh)
 	float one; // 1.0f; passed as data so that ptxas cannot fold the exact packed add p*one + q (chain_direct3.cuh)
 	// call scratch

@@ -36,7 +36,6 @@ using namespace b200s;
 
 static std::string g_createError;
 
-#define B200S_L2PF_DEFAULT 0 // bins per bulk L2 prefetch in k_chain_direct6 (0 = off)
 struct b200s_engine {
 	int S = 0, device = 0;
 	long seed = 0;
@@ -93,7 +92,6 @@ struct b200s_engine {
 	float *dMapB = 0, *dMapG = 0, *dRatio = 0, *dTE = 0;
 	float2 *dTPI = 0, *dTFT = 0, *dTT1 = 0, *dTT2 = 0;
 	int tFrames = 0;
-	int l2pf = -1;     // b200s_set_tuning key 6: k_chain_direct6, bins per bulk L2 prefetch of a spectrum row (0 = off; -1: B200S_L2PF or the default)
 	int dual = -1;     // b200s_set_tuning key 5: mono plain path, pairs of streams on the packed wavefront (-1: B200S_DUAL or on)
 	int stepMajor = 1; // b200s_set_tuning key 4: 0 = the round-1 kernels (k_prep + k_chain) for every stream
 	// random time factors beyond 2x stretch (:639-640): engine state per stream (lives as long as the handle, like the
@@ -175,15 +173,6 @@ static Ctx make_ctx(b200s_engine *e) {
 	x.rot = e->dRot; x.twiddle = e->dTwiddle; x.pretw = e->dPretw; x.anaTab = e->dAnaTab;
 	x.rot0 = e->rot0; x.rotStep = e->rotStep;
 	x.one = 1.0f;
-	{
-		static int env = -2;
-		if (env == -2) {
-			const char *v = getenv("B200S_L2PF");
-			env = v ? atoi(v) : -1;
-		}
-		const int want = e->l2pf >= 0 ? e->l2pf : env >= 0 ? env : B200S_L2PF_DEFAULT;
-		x.l2pf = (want >= 8 && (want & (want - 1)) == 0) ? want : 0;
-	}
 	x.sched = e->dSched;
 	x.histCur = e->dHist[e->histCur]; x.histNext = e->dHist[e->histCur ^ 1];
 	x.pend = e->dPend; x.pendWp = e->dPendWp;
@@ -382,6 +371,22 @@ static bool dual_enabled() {
 	return env != 0;
 }
 static ChainKernel chain3_kernel(const Cfg &g, int v, bool fast) {
+#ifdef B200S_CHAIN_PROBES // profiling builds only: ablations of k_chain_direct6 (wrong results), B200S_CHAIN_PROBE=1..4
+	if (v >= 6 && fast && g.L == 4) {
+		static int probe = -1;
+		if (probe < 0) {
+			const char *pv = getenv("B200S_CHAIN_PROBE");
+			probe = pv ? atoi(pv) : 0;
+		}
+		switch (probe) {
+		case 1: return k_chain_direct6<4, true, false, 1>;
+		case 2: return k_chain_direct6<4, true, false, 2>;
+		case 3: return k_chain_direct6<4, true, false, 3>;
+		case 4: return k_chain_direct6<4, true, false, 4>;
+		default: break;
+		}
+	}
+#endif
 	if (v >= 6) return fast ? chain6_kernel<true, false>(g.L) : chain6_kernel<false, false>(g.L);
 	if (v >= 4) return fast ? chain4_kernel<true>(g.L) : chain4_kernel<false>(g.L);
 #ifdef B200S_KEEP_OLD_KERNELS
@@ -1162,7 +1167,6 @@ int b200s_set_tuning(b200s_engine *e, int key, int value) {
 	else if (key == 3 && (value == 0 || value == 1)) e->exactMath = value;
 	else if (key == 4 && (value == 0 || value == 1)) e->stepMajor = value;
 	else if (key == 5 && (value == 0 || value == 1)) e->dual = value;
-	else if (key == 6 && (value == 0 || value == 8 || value == 16 || value == 32 || value == 64 || value == 128)) e->l2pf = value;
 	else {
 		e->err = "b200s_set_tuning: unknown key or value";
 		return B200S_EINVAL;
