@@ -52,11 +52,12 @@ __device__ __forceinline__ f2 ld_f2s(const float2 *p) {
 	return f2_make(v.x, v.y);
 }
 // Prediction::makeOutput (:596-603) where Prediction::energy is |input|^2 (plain path): the weak branch's norm is energy + noiseFloor
+// (sqrtE = sqrt(energy), taken one step ahead of its use: only the rsqrt of the phase's norm sits on the recurrence)
 template <int PROBE = 0>
-__device__ __forceinline__ float2 make_output_fast_e(float2 phase, float energy, float2 input) {
+__device__ __forceinline__ float2 make_output_fast_e(float2 phase, float energy, float sqrtE, float2 input) {
 	const float pn = ffma(phase.x, phase.x, phase.y * phase.y);
 	const bool weak = pn <= B200S_NOISE_FLOOR;
-	const float g = PROBE == 1 ? ffma(energy, 0.5f, weak ? energy + B200S_NOISE_FLOOR : pn) : sqrt_fast(energy) * rsqrt_fast(weak ? energy + B200S_NOISE_FLOOR : pn);
+	const float g = PROBE == 1 ? ffma(energy, 0.5f, weak ? energy + B200S_NOISE_FLOOR : pn) : sqrtE * rsqrt_fast(weak ? energy + B200S_NOISE_FLOOR : pn);
 	return make_float2((weak ? input.x : phase.x) * g, (weak ? input.y : phase.y) * g);
 }
 
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 		const float4 *prevInIl = nullptr, *myInIl = nullptr;
 		const float2 *prevInD0 = nullptr, *myInD[2] = {nullptr, nullptr};
 		ptrdiff_t prevInDD = 0;
-		float2 *ylA = nullptr, *ylB = nullptr; // Band::output rows of this lane's block: the two halves (channels, or streams A / B)
+		float2 *yBaseA = nullptr, *yBaseB = nullptr; // Band::output rows of block base (+ r: r rows on), the two halves (channels, or streams A / B)
 		float *eRowD[2] = {nullptr, nullptr};
 		if constexpr (DUAL) {
 			if (base > 0) {
@@ -139,15 +140,15 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 				U.rowPv[h][lane] = spec_slot(x, sH[h], fr.prevSlot, 0);
 				eRowD[h] = x.cE + coef_off(x, sH[h], active ? f : base, 0);
 			}
-			ylA = x.Y + coef_off(x, sH[0], active ? f : base, 0);
-			ylB = x.Y + coef_off(x, sH[1], active ? f : base, 0);
+			yBaseA = x.Y + coef_off(x, sH[0], base, 0); // mono: one row per block
+			yBaseB = x.Y + coef_off(x, sH[1], base, 0);
 		} else {
 			prevInIl = base == 0 ? nullptr : il_row(x, s, prevSlotIn);
 			myInIl = il_row(x, s, fr.inSlot);
 			U.rowIn[0][lane] = myInIl;
 			U.rowPv[0][lane] = il_row(x, s, fr.prevSlot);
-			ylA = x.Y + coef_off(x, s, active ? f : base, 0);
-			ylB = ylA + K;
+			yBaseA = x.Y + coef_off(x, s, base, 0); // stereo: two rows per block, channel 1 after channel 0
+			yBaseB = yBaseA + K;
 		}
 		const bool lastFrame = DUAL && active && f == cl.nFrames - 1; // its Prediction::energy is the state the next call continues from
 		__syncwarp();
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 		// latency (and the float -> int conversions in front of the addresses) overlaps the previous step's arithmetic instead
 		// of stalling this one (ncu, round 3: 10 % of the kernel's stall samples sat on the consumers of these loads).
 		c2 cLo2 = zc, cHi2 = zc, cLo1 = zc, cHi1 = zc, cInB = zc;
+		f2 cEB = z2, cSqB = z2; // Prediction::energy at bin b (= |input|^2 on this path, :679,:708) and, fast mode, its square root
 		float cF2s = 0.f, cF1s = 0.f;
 		auto preload = [&](const int qn, auto farTag, auto intTag, bool withRe) {
 			constexpr bool FAR = decltype(farTag)::value, INTERIOR = decltype(intTag)::value;
@@ -291,6 +293,12 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 			cF1s = fsub(i1, (float)l1);
 			if (withRe) cRe = ld_f2s(&U.eR[qn & (CH6_ER - 1)][0] + lane - (PROBE == 4 ? 0 : 1));
 			cInB = sel_c2(INTERIOR || (active && (unsigned)bn < (unsigned)K), ld_t<DUAL>(&U.in[bn & (CH3_RING - 1)][lane])); // Prediction::input at bin bn
+			if constexpr (FAST) {
+				cEB = fnorm2(cInB);
+				cSqB = PROBE == 1 ? cEB : f2_make(sqrt_fast(f2_lo(cEB)), sqrt_fast(f2_hi(cEB)));
+			} else {
+				cEB = xnorm2(cInB, one);
+			}
 			if constexpr (PROBE == 3) {
 				cLo2 = cHi2 = cLo1 = cHi1 = cInB;
 			} else if constexpr (!FAR) {
@@ -325,8 +333,8 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 			// ---------------- CHAIN_CH steps ----------------
 			// INTERIOR: every lane's q, b and interpolation points are inside [0, K) for the whole chunk, so all the
 			// edge masks below are identities and are compiled out (about nine chunks in ten)
-			auto step = [&](const int i, const int u, float2 *const sA, float2 *const sB, auto farTag, auto intTag, auto actTag) {
-				constexpr bool FAR = decltype(farTag)::value, INTERIOR = decltype(intTag)::value, ALLACT = decltype(actTag)::value;
+			auto step = [&](const int i, auto farTag, auto intTag) {
+				constexpr bool FAR = decltype(farTag)::value, INTERIOR = decltype(intTag)::value;
 				const int q = k0 + i - G * lane;
 				const int b = q - LT - 1, p2 = q - 1, p1 = q - D1;
 				const bool qIn = INTERIOR || (active && (unsigned)q < (unsigned)K);
@@ -336,14 +344,14 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 				// the previous block's final output / energy at bin q
 				const c2 lo2 = cLo2, hi2 = cHi2, lo1 = cLo1, hi1 = cHi1, inB = cInB;
 				const float f2s = cF2s, f1s = cF1s;
-				const f2 re = cRe;
+				const f2 re = cRe, eB = cEB, sqB = cSqB;
 				c2 ro = roN;
 				const c2 inq = ld_t<DUAL>(&U.in[q & (CH3_RING - 1)][lane]);
 				c2 pv = ld_t<DUAL>(&U.pvy[cb][i][lane]);
 				preload(q + 1, farTag, intTag, true); // ... and the same for the next step
 				const c2 in1 = D1 == 1 ? inP : inP2; // Prediction::input at bin p1
 				c2 newPre, T2, t1n;
-				f2 newE, eB;
+				f2 newE;
 				if constexpr (FAST) {
 					pv = fmul_s(pv, rotq); // :653-654 rotate Band::output and Band::prevInput by one interval
 					ro = fmul_s(ro, rotq);
@@ -355,7 +363,6 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 					newE = sel_f2(qIn, e);
 					T2 = sel_c2(p2In, fmulc_c(inP, flerp2(lo2, hi2, f2s)));  // long twist at p2 (:758)
 					t1n = sel_c2(p1In, fmulc_c(in1, flerp2(lo1, hi1, f1s))); // short twist at p1 (:751,:771)
-					eB = fnorm2(inB);
 				} else {
 					pv = xmul2s(pv, rotq, one);
 					ro = xmul2s(ro, rotq, one);
@@ -366,7 +373,6 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 					newE = sel_f2(qIn, e);
 					T2 = sel_c2(p2In, xmulc2(inP, xlerp2p(lo2, hi2, f2s, one), one));
 					t1n = sel_c2(p1In, xmulc2(in1, xlerp2p(lo1, hi1, f1s, one), one));
-					eB = xnorm2(inB, one);
 				}
 				{
 					const float2 st = make_float2(f2_lo(newE), f2_hi(newE));
@@ -407,17 +413,18 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 						if constexpr (A == 1) RF[1] = RF[1] + sel_c2(b + 1 < K - 1, fmulc_c(preA, t1A));
 					}
 					if constexpr (DUAL) { // :788, each half its own (mono) stream
-						const float2 oA = make_output_fast_e<PROBE>(pick(false, ph2), f2_lo(eB), pick(false, inB));
-						const float2 oB = make_output_fast_e<PROBE>(pick(true, ph2), f2_hi(eB), pick(true, inB));
+						const float2 oA = make_output_fast_e<PROBE>(pick(false, ph2), f2_lo(eB), f2_lo(sqB), pick(false, inB));
+						const float2 oB = make_output_fast_e<PROBE>(pick(true, ph2), f2_hi(eB), f2_hi(sqB), pick(true, inB));
 						oc = c2{f2_make(oA.x, oB.x), f2_make(oA.y, oB.y)};
 					} else { // the louder channel (first on ties, :733) leads, the other is locked in phase (:791-799)
 						const bool m = f2_hi(eB) > f2_lo(eB);
 						const float maxE = m ? f2_hi(eB) : f2_lo(eB);
 						const float2 phase = pick(m, ph2), pinM = pick(m, inB);
-						const float2 outM = make_output_fast_e<PROBE>(phase, maxE, pinM); // :788
+						const float sqM = m ? f2_hi(sqB) : f2_lo(sqB), sqO = m ? f2_lo(sqB) : f2_hi(sqB);
+						const float2 outM = make_output_fast_e<PROBE>(phase, maxE, sqM, pinM); // :788
 						const float2 inO = pick(!m, inB);
 						const float eO = m ? f2_lo(eB) : f2_hi(eB);
-						const float2 outO = PROBE == 2 ? outM : make_output_fast_e<PROBE>(fmul_f(outM, fmulc_f(inO, pinM)), eO, inO);
+						const float2 outO = PROBE == 2 ? outM : make_output_fast_e<PROBE>(fmul_f(outM, fmulc_f(inO, pinM)), eO, sqO, inO);
 						oc = c2{f2_make(m ? outO.x : outM.x, m ? outM.x : outO.x), f2_make(m ? outO.y : outM.y, m ? outM.y : outO.y)};
 					}
 				} else {
@@ -456,20 +463,11 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 #pragma unroll
 				for (int u = 0; u + 1 < LT; ++u) RF[u] = RF[u + 1];
 				RF[LT - 1] = rNew;
-				U.pvy[cb][i][lane] = pack_t<DUAL>(oc); // for the next lane (its prelim bin of the next step)
-				// Band::output of bin b goes straight to its rows, 8 bytes per half and step: L2 merges the four steps of a
-				// sector long before it is evicted, and the separate write-back pass at the end of every chunk (tile reads,
-				// address arithmetic, predicated stores: 14 % of the kernel's stall samples, ncu round 3) is gone
-				// (sA / sB: the slots of the final bins of the four unrolled steps, so the addresses are one base + immediates;
-				//  ALLACT: every lane of the warp owns a block, the common case -- nothing to guard in an interior chunk)
-				if ((ALLACT && INTERIOR) || (active && (INTERIOR || (unsigned)b < (unsigned)K))) {
-					sA[u] = make_float2(f2_lo(oc.re), f2_lo(oc.im));
-					sB[u] = make_float2(f2_hi(oc.re), f2_hi(oc.im));
-					if constexpr (DUAL) {
-						if (lastFrame) {
-							eRowD[0][b] = f2_lo(eB);
-							eRowD[1][b] = f2_hi(eB);
-						}
+				U.pvy[cb][i][lane] = pack_t<DUAL>(oc); // for the next lane (its prelim bin of the next step) and for the write-back
+				if constexpr (DUAL) {
+					if (lastFrame && (unsigned)b < (unsigned)K) {
+						eRowD[0][b] = f2_lo(eB);
+						eRowD[1][b] = f2_hi(eB);
 					}
 				}
 				__syncwarp();
@@ -477,20 +475,36 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 			};
 			// unrolled by 4 (for L = 4 the register FIFOs rotate by pure renaming) so that the hot loop stays in the
 			// instruction cache; branch-free inside
-			auto run_chunk = [&](auto farTag, auto intTag, auto actTag) {
-				float2 *const cA = ylA + (k0 - G * lane - LT - 1), *const cB = ylB + (k0 - G * lane - LT - 1); // slot of step 0's final bin
+			auto run_chunk = [&](auto farTag, auto intTag) {
 #pragma unroll 1
 				for (int h = 0; h < CHAIN_CH; h += 4) {
-					float2 *const sA = cA + h, *const sB = cB + h;
 #pragma unroll
-					for (int u = 0; u < 4; ++u) step(h + u, u, sA, sB, farTag, intTag, actTag);
+					for (int u = 0; u < 4; ++u) step(h + u, farTag, intTag);
 				}
 			};
-			if (farAny) run_chunk(std::true_type{}, std::false_type{}, std::false_type{});
-			else if (k0 >= interiorFrom && k0 + CHAIN_CH <= K) {
-				if (nAct == 32) run_chunk(std::false_type{}, std::true_type{}, std::true_type{});
-				else run_chunk(std::false_type{}, std::true_type{}, std::false_type{});
-			} else run_chunk(std::false_type{}, std::false_type{}, std::false_type{});
+			if (farAny) run_chunk(std::true_type{}, std::false_type{});
+			else if (k0 >= interiorFrom && k0 + CHAIN_CH <= K) run_chunk(std::false_type{}, std::true_type{});
+			else run_chunk(std::false_type{}, std::false_type{});
+			// ---------------- write the chunk's finals back: planar Band::output rows, 32 B per row and quarter-warp;
+			//                  all tile reads first, then the stores (row addresses are arithmetic).
+			// (Measured dead end, round 3: every lane storing its own final straight to its row in every step -- 64 partial-
+			//  sector writes per warp and step instead of 16 full-sector stores per chunk: 2.62 ms against 1.68 ms.)
+			{
+				float4 v[8];
+#pragma unroll
+				for (int it = 0; it < 8; ++it) v[it] = U.pvy[cb][fillI][fillF + 4 * it];
+				const int rowMul = DUAL ? 1 : 2; // rows per block in Y
+#pragma unroll
+				for (int it = 0; it < 8; ++it) {
+					const int fl = fillF + 4 * it;
+					const int b = k0 + fillI - G * fl - LT - 1;
+					if (fl < nAct && (unsigned)b < (unsigned)K) {
+						const size_t o = (size_t)(rowMul * fl) * K + b;
+						yBaseA[o] = make_float2(v[it].x, v[it].z);
+						yBaseB[o] = make_float2(v[it].y, v[it].w);
+					}
+				}
+			}
 			__syncwarp();
 		}
 	}
