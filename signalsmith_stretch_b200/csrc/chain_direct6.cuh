@@ -2,7 +2,7 @@
 // instruction diet, for stereo streams (DUAL = false) and for PAIRS OF MONO STREAMS (DUAL = true).
 //
 // k_chain_direct4 spends 186 SASS instructions per step on its interior path, of which only ~55 % are arithmetic
-// (cuobjdump, round 3): 35 MOVs (its five-entry register FIFOs do not rotate by renaming in a loop unrolled by four),
+// (cuobjdump, round 2): 35 MOVs (its five-entry register FIFOs do not rotate by renaming in a loop unrolled by four),
 // 6 SHFL + 6 FSEL for the lane-to-lane hand-off (lane 0 takes its predecessor from shared memory instead), 15 shared-
 // memory instructions.  Here
 //   * every FIFO has exactly L entries, so for L = 4 (both presets) the loop unrolled by four rotates them by pure
@@ -64,6 +64,7 @@ __device__ __forceinline__ float2 make_output_fast_e(float2 phase, float energy,
 // PROBE (profiling builds only, results are WRONG): ablations that time what a part of the step costs --
 //   1: no SFU (rcp / rsqrt / sqrt replaced by one FMA)   2: the locked channel copies the leader (no second makeOutput)
 //   3: no interpolation loads (the twists use the prelim bin's input)   4: no lane-to-lane hand-off (every lane re-reads its own slots)
+//   5: the previous-input spectrum is not fetched (half the reads)   6: the finals are not written back   7: 5 + 6 + no input fetch either
 template <int LT, bool FAST, bool DUAL, int PROBE = 0>
 __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 	const Cfg &g = x.cfg;
@@ -230,8 +231,8 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 					const int fl = fillF + 4 * it;
 					const int q = kf + fillI - G * fl;
 					if (fl < nAct && (unsigned)q < (unsigned)K) {
-						cp_async16(&U.in[q & (CH3_RING - 1)][fl], rIn[it] + q);
-						cp_async16(&U.pvy[buf][fillI][fl], rPv[it] + q);
+						if (PROBE != 7) cp_async16(&U.in[q & (CH3_RING - 1)][fl], rIn[it] + q);
+						if (PROBE != 5 && PROBE != 7) cp_async16(&U.pvy[buf][fillI][fl], rPv[it] + q);
 					}
 				}
 			}
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 		// Everything a step reads from BEHIND its prelim bin -- the interpolation points of the two twists, Prediction::input of
 		// the final bin, the predecessor's energy -- is loaded ONE STEP AHEAD into these registers, so that the shared-memory
 		// latency (and the float -> int conversions in front of the addresses) overlaps the previous step's arithmetic instead
-		// of stalling this one (ncu, round 3: 10 % of the kernel's stall samples sat on the consumers of these loads).
+		// of stalling this one (ncu, round 2, profiles/r02_chain6_ab.md: 10 % of the kernel's stall samples sat on the consumers of these loads).
 		c2 cLo2 = zc, cHi2 = zc, cLo1 = zc, cHi1 = zc, cInB = zc;
 		f2 cEB = z2, cSqB = z2; // Prediction::energy at bin b (= |input|^2 on this path, :679,:708) and, fast mode, its square root
 		float cF2s = 0.f, cF1s = 0.f;
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 			else run_chunk(std::false_type{}, std::false_type{});
 			// ---------------- write the chunk's finals back: planar Band::output rows, 32 B per row and quarter-warp;
 			//                  all tile reads first, then the stores (row addresses are arithmetic).
-			// (Measured dead end, round 3: every lane storing its own final straight to its row in every step -- 64 partial-
+			// (Measured dead end, round 2: every lane storing its own final straight to its row in every step -- 64 partial-
 			//  sector writes per warp and step instead of 16 full-sector stores per chunk: 2.62 ms against 1.68 ms.)
 			{
 				float4 v[8];
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 				for (int it = 0; it < 8; ++it) {
 					const int fl = fillF + 4 * it;
 					const int b = k0 + fillI - G * fl - LT - 1;
-					if (fl < nAct && (unsigned)b < (unsigned)K) {
+					if (PROBE != 6 && PROBE != 7 && fl < nAct && (unsigned)b < (unsigned)K) {
 						const size_t o = (size_t)(rowMul * fl) * K + b;
 						yBaseA[o] = make_float2(v[it].x, v[it].z);
 						yBaseB[o] = make_float2(v[it].y, v[it].w);

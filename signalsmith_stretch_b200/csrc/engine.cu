@@ -359,7 +359,7 @@ static ChainKernel chain6_kernel(int L) {
 	}
 }
 // mono plain path: pairs of streams on the packed wavefront (k_chain_direct6<.., DUAL>) instead of k_chain_direct2.  Off by
-// default: measured on B200 (profiles/r03_chain6_ab.md) it is no faster (4.99 vs 4.85 ms for 4096 streams) although it issues
+// default: measured on B200 (profiles/r02_chain6_ab.md) it is no faster (4.99 vs 4.85 ms for 4096 streams) although it issues
 // 40 % fewer instructions per stream -- the wavefront kernels are bound by dependent latency at 7 warps per SM, not by issue.
 // B200S_DUAL=1 / b200s_set_tuning(e, 5, 1) switch it on (cross-check in the tests).
 static bool dual_enabled() {
@@ -371,7 +371,7 @@ static bool dual_enabled() {
 	return env != 0;
 }
 static ChainKernel chain3_kernel(const Cfg &g, int v, bool fast) {
-#ifdef B200S_CHAIN_PROBES // profiling builds only: ablations of k_chain_direct6 (wrong results), B200S_CHAIN_PROBE=1..4
+#ifdef B200S_CHAIN_PROBES // profiling builds only: ablations of k_chain_direct6 (wrong results), B200S_CHAIN_PROBE=1..7
 	if (v >= 6 && fast && g.L == 4) {
 		static int probe = -1;
 		if (probe < 0) {
@@ -383,6 +383,9 @@ static ChainKernel chain3_kernel(const Cfg &g, int v, bool fast) {
 		case 2: return k_chain_direct6<4, true, false, 2>;
 		case 3: return k_chain_direct6<4, true, false, 3>;
 		case 4: return k_chain_direct6<4, true, false, 4>;
+		case 5: return k_chain_direct6<4, true, false, 5>;
+		case 6: return k_chain_direct6<4, true, false, 6>;
+		case 7: return k_chain_direct6<4, true, false, 7>;
 		default: break;
 		}
 	}
