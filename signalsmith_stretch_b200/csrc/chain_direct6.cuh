@@ -30,16 +30,13 @@
 
 namespace b200s {
 
-#define CH6_Q 4                  // steps per chunk
-#define CH6_NB 4                 // chunk buffers of the previous-input / finals tile
-#define CH6_DIST 3               // chunks a fill runs ahead of the chunk it is for (ring: 14 bins back + 4 + 3 * 4 ahead <= 32)
 #define CH6_ER 16                // bins of the Prediction::energy ring (>= G + 1 and >= 2 chunks for lane 0's pads)
 #define CH6_FAR (CH4_FAR - 1)    // the twists are formed one bin later than in k_chain_direct4: one bin less reach
 
 struct Chain6Tiles {
 	float4 in[CH3_RING][CH3_RS];     // rolling window of each block's input spectrum, [bin & 31][lane]
 	float4 lead[2];                  // lead[1] is the "lane -1" slot of pvy[0][0]
-	float4 pvy[CH6_NB][CH6_Q][CH3_RS]; // previous-input spectrum at the chunk's bins, overwritten by the finals of the same step;
+	float4 pvy[2][CHAIN_CH][CH3_RS]; // previous-input spectrum at the chunk's bins, overwritten by the finals of the same step;
 	                                 // slot [..][i][-1] (= the padding of the row before): lane 0's predecessor for the NEXT step
 	float2 eLead[2];                 // eLead[1] is the "lane -1" slot of eR[0]
 	float2 eR[CH6_ER][CH3_RS];       // Prediction::energy at bin q of each block, [bin & 15][lane]; [..][-1]: lane 0's predecessor
@@ -81,11 +78,10 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 	const bool pairOk = DUAL && dual_pair_ok(x, s0, lane);
 	const int nPass = (DUAL && !pairOk && s0 + 1 < x.sBase + x.sCount) ? 2 : 1;
 	constexpr int G = LT + 2; // lane skew in bins
-	static_assert(G + 1 <= CH6_ER && (CH6_DIST + 1) * CH6_Q <= CH6_ER, "energy ring too short");
-	static_assert(CH6_FAR + 3 + (CH6_DIST + 1) * CH6_Q <= CH3_RING && CH6_DIST < CH6_NB, "spectrum ring too short for the fills in flight");
+	static_assert(G + 1 <= CH6_ER && 2 * CHAIN_CH <= CH6_ER, "energy ring too short");
 	Chain6Tiles &U = *(Chain6Tiles *)dyn_smem;
-	// chunk fill: lane -> (bin offset within the chunk, row within a group of 8); four lanes cover the 4 bins (64 B) of a row
-	const int fillI = lane & 3, fillF = lane >> 2;
+	// chunk fill: lane -> (bin offset, row within a group of 4); a quarter-warp covers 4 bins (64 B) of 2 rows
+	const int fillI = (lane & 3) | (((lane >> 3) & 1) << 2), fillF = ((lane >> 2) & 1) | (((lane >> 4) & 1) << 1);
 	const float2 rot0 = x.rot0, rotStep = x.rotStep;
 	const float one = x.one; // 1.0f, opaque to the compiler (see padd / psub)
 	const f2 z2 = f2_make(0.f, 0.f);
@@ -196,18 +192,18 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 		// progress (other buffer / other half of the ring).
 		auto fill = [&](int kf, int buf) {
 			if constexpr (DUAL) {
-				const float2 *rIn[2][4], *rPv[2][4];
+				const float2 *rIn[2][8], *rPv[2][8];
 #pragma unroll
-				for (int it = 0; it < 4; ++it) {
+				for (int it = 0; it < 8; ++it) {
 #pragma unroll
 					for (int h = 0; h < 2; ++h) {
-						rIn[h][it] = (const float2 *)U.rowIn[h][fillF + 8 * it];
-						rPv[h][it] = (const float2 *)U.rowPv[h][fillF + 8 * it];
+						rIn[h][it] = (const float2 *)U.rowIn[h][fillF + 4 * it];
+						rPv[h][it] = (const float2 *)U.rowPv[h][fillF + 4 * it];
 					}
 				}
 #pragma unroll
-				for (int it = 0; it < 4; ++it) {
-					const int fl = fillF + 8 * it;
+				for (int it = 0; it < 8; ++it) {
+					const int fl = fillF + 4 * it;
 					const int q = kf + fillI - G * fl;
 					if (fl < nAct && (unsigned)q < (unsigned)K) {
 						// slot = {A.re, B.re, A.im, B.im}: the layout the packed arithmetic wants (as the interleaved stereo spectra),
@@ -216,27 +212,23 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 						for (int h = 0; h < 2; ++h) {
 							float *dIn = (float *)&U.in[q & (CH3_RING - 1)][fl] + h, *dPv = (float *)&U.pvy[buf][fillI][fl] + h;
 							const float *sIn = (const float *)(rIn[h][it] + q), *sPv = (const float *)(rPv[h][it] + q);
-							if (PROBE != 7) {
-								cp_async4(dIn, sIn);
-								cp_async4(dIn + 2, sIn + 1);
-							}
-							if (PROBE != 5 && PROBE != 7) {
-								cp_async4(dPv, sPv);
-								cp_async4(dPv + 2, sPv + 1);
-							}
+							cp_async4(dIn, sIn);
+							cp_async4(dIn + 2, sIn + 1);
+							cp_async4(dPv, sPv);
+							cp_async4(dPv + 2, sPv + 1);
 						}
 					}
 				}
 			} else {
-				const float4 *rIn[4], *rPv[4];
+				const float4 *rIn[8], *rPv[8];
 #pragma unroll
-				for (int it = 0; it < 4; ++it) {
-					rIn[it] = (const float4 *)U.rowIn[0][fillF + 8 * it];
-					rPv[it] = (const float4 *)U.rowPv[0][fillF + 8 * it];
+				for (int it = 0; it < 8; ++it) {
+					rIn[it] = (const float4 *)U.rowIn[0][fillF + 4 * it];
+					rPv[it] = (const float4 *)U.rowPv[0][fillF + 4 * it];
 				}
 #pragma unroll
-				for (int it = 0; it < 4; ++it) {
-					const int fl = fillF + 8 * it;
+				for (int it = 0; it < 8; ++it) {
+					const int fl = fillF + 4 * it;
 					const int q = kf + fillI - G * fl;
 					if (fl < nAct && (unsigned)q < (unsigned)K) {
 						if (PROBE != 7) cp_async16(&U.in[q & (CH3_RING - 1)][fl], rIn[it] + q);
@@ -244,12 +236,13 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 					}
 				}
 			}
-			if (lane < 4 * CH6_Q) { // lane 0's predecessor finals: 4 floats per bin, one 4-byte copy per lane
+			{ // lane 0's predecessor finals: 4 floats per bin, one 4-byte copy per lane
 				const int i = lane >> 2, comp = lane & 3, qq = kf + 1 + i;
 				const int h = comp & 1, part = comp >> 1; // tile slot component {re0, re1, im0, im1} -> (half, re / im)
 				if (qq < K) cp_async4((float *)(&U.pvy[buf][i][0] - 1) + comp, (const float *)(prevOut0 + h * prevOutD + qq) + part);
-			} else if (lane < 6 * CH6_Q) { // ... and its Prediction::energy {half 0, half 1}, the same bins (read one step ahead, too)
-				const int qq = kf + 1 + ((lane - 4 * CH6_Q) >> 1), h = lane & 1;
+			}
+			if (lane < 2 * CHAIN_CH) { // ... and its Prediction::energy {half 0, half 1}, bins kf+1 .. kf+8 (read one step ahead, too)
+				const int qq = kf + 1 + (lane >> 1), h = lane & 1;
 				float *pad = (float *)(&U.eR[qq & (CH6_ER - 1)][0] - 1) + h;
 				if (qq < K) {
 					if (base == 0) {
@@ -262,10 +255,8 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 					}
 				}
 			}
-			cp_async_commit(); // one group per chunk (also when nothing was copied: the waits count groups)
 		};
-#pragma unroll
-		for (int d = 0; d < CH6_DIST; ++d) fill(CH6_Q * d, d);
+		fill(0, 0);
 		// final output of the previous block at the prelim bin of the NEXT step (read from the tile at the end of each step);
 		// for the first step: lane 0's predecessor at bin 0, nothing for the others (their q is negative)
 		c2 roN = zc;
@@ -336,11 +327,11 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 		if (farAny) preload(-G * lane, std::true_type{}, std::false_type{}, false);
 		else preload(-G * lane, std::false_type{}, std::false_type{}, false);
 		int cb = 0; // buffer of the chunk being computed
-		for (int k0 = 0; k0 < steps; k0 += CH6_Q, cb = (cb + 1) & (CH6_NB - 1)) {
-			cp_async_wait_group<CH6_DIST - 1>(); // this chunk's tiles (issued CH6_DIST chunks ago; the younger fills stay in flight)
+		for (int k0 = 0; k0 < steps; k0 += CHAIN_CH, cb ^= 1) {
+			cp_async_wait_all(); // this chunk's tiles (issued one chunk ago)
 			__syncwarp();
-			fill(k0 + CH6_Q * CH6_DIST, (cb + CH6_DIST) & (CH6_NB - 1)); // in flight during the next CH6_DIST chunks (masked beyond K)
-			// ---------------- CH6_Q steps ----------------
+			if (k0 + CHAIN_CH < steps) fill(k0 + CHAIN_CH, cb ^ 1); // next chunk: in flight during the 8 steps below
+			// ---------------- CHAIN_CH steps ----------------
 			// INTERIOR: every lane's q, b and interpolation points are inside [0, K) for the whole chunk, so all the
 			// edge masks below are identities and are compiled out (about nine chunks in ten)
 			auto step = [&](const int i, auto farTag, auto intTag) {
@@ -486,24 +477,27 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 			// unrolled by 4 (for L = 4 the register FIFOs rotate by pure renaming) so that the hot loop stays in the
 			// instruction cache; branch-free inside
 			auto run_chunk = [&](auto farTag, auto intTag) {
+#pragma unroll 1
+				for (int h = 0; h < CHAIN_CH; h += 4) {
 #pragma unroll
-				for (int u = 0; u < CH6_Q; ++u) step(u, farTag, intTag);
+					for (int u = 0; u < 4; ++u) step(h + u, farTag, intTag);
+				}
 			};
 			if (farAny) run_chunk(std::true_type{}, std::false_type{});
-			else if (k0 >= interiorFrom && k0 + CH6_Q <= K) run_chunk(std::false_type{}, std::true_type{});
+			else if (k0 >= interiorFrom && k0 + CHAIN_CH <= K) run_chunk(std::false_type{}, std::true_type{});
 			else run_chunk(std::false_type{}, std::false_type{});
 			// ---------------- write the chunk's finals back: planar Band::output rows, 32 B per row and quarter-warp;
 			//                  all tile reads first, then the stores (row addresses are arithmetic).
 			// (Measured dead end, round 2: every lane storing its own final straight to its row in every step -- 64 partial-
 			//  sector writes per warp and step instead of 16 full-sector stores per chunk: 2.62 ms against 1.68 ms.)
 			{
-				float4 v[4];
+				float4 v[8];
 #pragma unroll
-				for (int it = 0; it < 4; ++it) v[it] = U.pvy[cb][fillI][fillF + 8 * it];
+				for (int it = 0; it < 8; ++it) v[it] = U.pvy[cb][fillI][fillF + 4 * it];
 				const int rowMul = DUAL ? 1 : 2; // rows per block in Y
 #pragma unroll
-				for (int it = 0; it < 4; ++it) {
-					const int fl = fillF + 8 * it;
+				for (int it = 0; it < 8; ++it) {
+					const int fl = fillF + 4 * it;
 					const int b = k0 + fillI - G * fl - LT - 1;
 					if (PROBE != 6 && PROBE != 7 && fl < nAct && (unsigned)b < (unsigned)K) {
 						const size_t o = (size_t)(rowMul * fl) * K + b;
