@@ -239,11 +239,7 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 			{ // lane 0's predecessor finals: 4 floats per bin, one 4-byte copy per lane
 				const int i = lane >> 2, comp = lane & 3, qq = kf + 1 + i;
 				const int h = comp & 1, part = comp >> 1; // tile slot component {re0, re1, im0, im1} -> (half, re / im)
-				if (!DUAL && x.yIl && base > 0) { // the previous group's rows are interleaved like the tile slots: one 16-byte copy per bin
-					if (comp == 0 && qq < K) cp_async16(&U.pvy[buf][i][0] - 1, (const float4 *)prevOut0 + qq);
-				} else if (qq < K) {
-					cp_async4((float *)(&U.pvy[buf][i][0] - 1) + comp, (const float *)(prevOut0 + h * prevOutD + qq) + part);
-				}
+				if (qq < K) cp_async4((float *)(&U.pvy[buf][i][0] - 1) + comp, (const float *)(prevOut0 + h * prevOutD + qq) + part);
 			}
 			if (lane < 2 * CHAIN_CH) { // ... and its Prediction::energy {half 0, half 1}, bins kf+1 .. kf+8 (read one step ahead, too)
 				const int qq = kf + 1 + (lane >> 1), h = lane & 1;
@@ -266,12 +262,8 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 		c2 roN = zc;
 		f2 cRe = z2; // ... and its Prediction::energy at that bin
 		if (lane == 0) {
-			if (!DUAL && x.yIl && base > 0) {
-				roN = ld_c2s((const float4 *)prevOut0);
-			} else {
-				const float2 a = prevOut0[0], bb = prevOut0[prevOutD];
-				roN = c2{f2_make(a.x, bb.x), f2_make(a.y, bb.y)};
-			}
+			const float2 a = prevOut0[0], bb = prevOut0[prevOutD];
+			roN = c2{f2_make(a.x, bb.x), f2_make(a.y, bb.y)};
 			if (base == 0) {
 				cRe = f2_make(prevE0[0], prevE0[prevED]);
 			} else if constexpr (DUAL) {
@@ -509,12 +501,8 @@ __global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 					const int b = k0 + fillI - G * fl - LT - 1;
 					if (PROBE != 6 && PROBE != 7 && fl < nAct && (unsigned)b < (unsigned)K) {
 						const size_t o = (size_t)(rowMul * fl) * K + b;
-						if (!DUAL && x.yIl) { // interleaved rows: the tile slot as it is, 128 contiguous bytes per row and chunk
-							((float4 *)yBaseA)[(size_t)fl * K + b] = v[it];
-						} else {
-							yBaseA[o] = make_float2(v[it].x, v[it].z);
-							yBaseB[o] = make_float2(v[it].y, v[it].w);
-						}
+						yBaseA[o] = make_float2(v[it].x, v[it].z);
+						yBaseB[o] = make_float2(v[it].y, v[it].w);
 					}
 				}
 			}

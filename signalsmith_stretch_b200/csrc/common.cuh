@@ -120,8 +120,6 @@ struct Ctx {
 	// stIl [S][2][K] holds such copies of stIn / stPrev, made by k_plan at the start of the call
 	float4 *stIl;
 	int specIl;
-	int yIl;   // the Band::output rows of this call (Y) are channel-interleaved float4 {re0, re1, im0, im1} per bin, like the stereo spectra:
-	           // k_chain_direct6 then writes back 128-byte pieces instead of two 64-byte ones (k_synth2 / k_commit pick their channel)
 	int wsRan; // k_chain_ws ran before k_chain_direct4 in this call: the latter only takes the streams the former left (chain_ws.cuh)
 	float one; // 1.0f; passed as data so that ptxas cannot fold the exact packed add p*one + q (chain_direct3.cuh)
 	// call scratch

@@ -362,15 +362,6 @@ static ChainKernel chain6_kernel(int L) {
 // default: measured on B200 (profiles/r02_chain6_ab.md) it is no faster (4.99 vs 4.85 ms for 4096 streams) although it issues
 // 40 % fewer instructions per stream -- the wavefront kernels are bound by dependent latency at 7 warps per SM, not by issue.
 // B200S_DUAL=1 / b200s_set_tuning(e, 5, 1) switch it on (cross-check in the tests).
-// k_chain_direct6: channel-interleaved Band::output rows (B200S_YIL=0 switches them off: A/B)
-static bool yil_enabled() {
-	static int env = -1;
-	if (env < 0) {
-		const char *v = getenv("B200S_YIL");
-		env = v ? (atoi(v) != 0) : 1;
-	}
-	return env != 0;
-}
 static bool dual_enabled() {
 	static int env = -1;
 	if (env < 0) {
@@ -810,8 +801,6 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 	const int chainV = chain_version(g, e->chainV, e->fftV1);
 	const bool pairFft = use_pair_fft(g, e->fftV1);
 	x.specIl = (plain && chainV >= 3) ? 1 : 0;
-	// generation 6 alone on the call (no stream can take the random path, whose generic chain writes planar rows): interleaved Y
-	x.yIl = (x.specIl && chainV >= 6 && !mayRandom && yil_enabled()) ? 1 : 0;
 	for (int sub = 0; sub < nSub; ++sub) {
 		cudaStream_t st = nSub > 1 ? e->subStream[sub] : e->stream;
 		if (nSub > 1 && !chained) CK(cudaStreamWaitEvent(st, e->evBegin, 0));

@@ -23,7 +23,6 @@ __host__ __device__ __forceinline__ int stage_len(int B) { return (B + 8 + 3) & 
 // large enough for the window / twiddle tables that every item re-reads
 #ifdef B200S_EMU
 __device__ __forceinline__ float2 ld_stream(const float2 *p) { return *p; }
-__device__ __forceinline__ float4 ld_stream4(const float4 *p) { return *p; }
 __device__ __forceinline__ void st_stream(float *p, float v) { *p = v; }
 __device__ __forceinline__ void st_stream4(float *p, float4 v) { *(float4 *)p = v; }
 #else
@@ -31,11 +30,6 @@ __device__ __forceinline__ void st_stream4(float *p, float4 v) { __stcs((float4 
 __device__ __forceinline__ float2 ld_stream(const float2 *p) {
 	float2 v;
 	asm volatile("ld.global.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-	return v;
-}
-__device__ __forceinline__ float4 ld_stream4(const float4 *p) {
-	float4 v;
-	asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
 	return v;
 }
 __device__ __forceinline__ void st_stream(float *p, float v) { __stcs(p, v); }
@@ -317,15 +311,12 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 		// samples emitted between the two blocks; without a second block nothing is emitted inside the sweep
 		const int gap = hasB ? frames[f + 1].t - tA : 0;
 		const float2 *YA = x.Y + coef_off(x, s, f, c), *YB = x.Y + coef_off(x, s, hasB ? f + 1 : f, c);
-		// interleaved Band::output rows (Ctx::yIl): one float4 {re0, re1, im0, im1} per bin, this CTA takes channel c of it
-		const float4 *YA4 = (const float4 *)(x.Y + coef_off(x, s, f, 0)), *YB4 = (const float4 *)(x.Y + coef_off(x, s, hasB ? f + 1 : f, 0));
 #ifndef B200S_EMU
 		// the spectra of the NEXT pair of blocks start their way from HBM to L2 now (two rows of 8*K bytes, one 128-byte
 		// line per thread and step), so that the loads at the top of the next iteration find them there
 		if (f + 2 < cl.nFrames) {
-			const int cc = x.yIl ? 0 : c, rowBytes = x.yIl ? KT * 16 : KT * 8;
-			const char *nA = (const char *)(x.Y + coef_off(x, s, f + 2, cc)), *nB = (const char *)(x.Y + coef_off(x, s, min(f + 3, cl.nFrames - 1), cc));
-			for (int o2 = tid * 128; o2 < rowBytes; o2 += 256 * 128) {
+			const char *nA = (const char *)(x.Y + coef_off(x, s, f + 2, c)), *nB = (const char *)(x.Y + coef_off(x, s, min(f + 3, cl.nFrames - 1), c));
+			for (int o2 = tid * 128; o2 < KT * 8; o2 += 256 * 128) {
 				asm volatile("prefetch.global.L2 [%0];" ::"l"(nA + o2));
 				asm volatile("prefetch.global.L2 [%0];" ::"l"(nB + o2));
 			}
@@ -341,15 +332,7 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 				const int k = q * G::M1 + tid;
 				const int b = q < 8 ? 2 * k : 2 * (KT - 1 - k) + 1;
 				const float sg = q < 8 ? 1.f : -1.f;
-				float2 a, bb;
-				if (x.yIl) {
-					const float4 a4 = ld_stream4(YA4 + b), b4 = ld_stream4(YB4 + b);
-					a = c ? make_float2(a4.y, a4.w) : make_float2(a4.x, a4.z);
-					bb = c ? make_float2(b4.y, b4.w) : make_float2(b4.x, b4.z);
-				} else {
-					a = ld_stream(YA + b);
-					bb = ld_stream(YB + b);
-				}
+				const float2 a = ld_stream(YA + b), bb = ld_stream(YB + b);
 				v[q] = c2{f2_make(a.x, bb.x), f2_make(sg * a.y, sg * bb.y)};
 			});
 		}
@@ -359,19 +342,8 @@ __global__ void __launch_bounds__(256, 2) k_synth2(Ctx x) {
 		float *yTimeA = (float *)buf, *yTimeB = yTimeA + B;
 		__syncthreads();
 		if (tid == 0) {
-			float2 *tA = nullptr, *tB = nullptr;
-			if (x.yIl) { // de-interleave this channel's rows for the oracle's transform
-				tA = new float2[KT];
-				tB = new float2[KT];
-				for (int b = 0; b < KT; ++b) {
-					tA[b] = c ? make_float2(YA4[b].y, YA4[b].w) : make_float2(YA4[b].x, YA4[b].z);
-					tB[b] = c ? make_float2(YB4[b].y, YB4[b].w) : make_float2(YB4[b].x, YB4[b].z);
-				}
-			}
-			emu_exact_inverse(x.yIl ? tA : YA, B, o, g.N, yTimeA);
-			if (hasB) emu_exact_inverse(x.yIl ? tB : YB, B, o, g.N, yTimeB);
-			delete[] tA;
-			delete[] tB;
+			emu_exact_inverse(YA, B, o, g.N, yTimeA);
+			if (hasB) emu_exact_inverse(YB, B, o, g.N, yTimeB);
 			for (int i = 0; i < B; ++i) { // the synthesis window is applied where the block is written (see below)
 				yTimeA[i] = fmul(yTimeA[i], x.window[i]);
 				if (hasB) yTimeB[i] = fmul(yTimeB[i], x.window[i]);
