@@ -1,19 +1,23 @@
 // chain_direct6.cuh -- k_chain_direct6: the packed frame wavefront of k_chain_direct4 (reference :722-804) on an
-// instruction diet, for stereo streams (DUAL = false) and for PAIRS OF MONO STREAMS (DUAL = true).
+// instruction diet, for stereo streams (DUAL = false) and for PAIRS OF MONO STREAMS (DUAL = true).  Selectable
+// (b200s_set_tuning key 0 = 6, key 5 = 1 for the mono pairs); generation 4 / k_chain_direct2 stay the defaults because this
+// kernel is no faster -- which is its result: see the end of this comment, DESIGN.md 3.8 and profiles/r02_chain6_ab.md.
 //
 // k_chain_direct4 spends 186 SASS instructions per step on its interior path, of which only ~55 % are arithmetic
 // (cuobjdump, round 2): 35 MOVs (its five-entry register FIFOs do not rotate by renaming in a loop unrolled by four),
 // 6 SHFL + 6 FSEL for the lane-to-lane hand-off (lane 0 takes its predecessor from shared memory instead), 15 shared-
 // memory instructions.  Here
-//   * every FIFO has exactly L entries, so for L = 4 (both presets) the loop unrolled by four rotates them by pure
-//     renaming: the long and the short vertical twists (:750-758) are formed ONE BIN BEHIND the preliminary prediction
-//     (at bin q-1, from the previous step's input) -- the long twist is then consumed in the same step (as the twist of
-//     bin b+L, :784) and L steps later (bin b, :761), the short twist L-1 and L steps later (:774, :754);
+//   * every FIFO has at most L entries and every value dies before its slot is rewritten, so for L = 4 (both presets)
+//     the loop unrolled by four rotates them by pure renaming: the long vertical twist (:758) is formed ONE BIN BEHIND
+//     the preliminary prediction and multiplied into its two products at once (out(b) * T2(b+L), :761, enters a product /
+//     accumulator FIFO when out(b) is finalised; pre(b+L) * conj(T2(b+L)), :784, is consumed in the same step), the short
+//     twist (:751) TWO bins behind (its :774 product runs one step ahead);
 //   * Prediction::input / energy of bin b are re-read from the rolling spectrum window (one LDS.128) instead of
 //     travelling through five-entry FIFOs;
 //   * the final output of a step goes to the tile slot it is written back from anyway, and the NEXT lane reads it from
 //     there ([lane-1], one LDS.128): no shuffles, no selects -- lane 0's predecessor block sits in the padding slot
-//     before each tile row, put there by the chunk fill; Prediction::energy travels the same way through a 16-bin ring.
+//     before each tile row, put there by the chunk fill; Prediction::energy travels the same way through a 16-bin ring;
+//   * everything a step reads from behind its prelim bin is loaded one step ahead.
 // Arithmetic, masks and operation order are those of k_chain_direct4 (exact mode: bit-identical, tested under
 // emulation and on the GPU); the fast mode additionally uses energy + noiseFloor for |input|^2 + noiseFloor in
 // makeOutput (:599; on this path Prediction::energy IS |input|^2, :679,:708).
@@ -21,9 +25,15 @@
 // DUAL: a mono batch has no second channel to pack -- but it has a second STREAM: lane j runs block j of stream 2p in
 // the low halves of its f32x2 registers and block j of stream 2p+1 in the high halves; the halves never meet (no
 // loudest-channel choice, no phase lock, each half its own makeOutput :788).  The two streams must walk the same
-// schedule in this call (dual_pair_ok, chain_direct2.cuh); pairs that do not, and the odd stream of an odd batch, are
-// left to k_chain_direct2, which skips the pairs taken here.  Spectra stay planar (mono analysis is unchanged): the
+// schedule in this call (dual_pair_ok, chain_direct2.cuh); pairs that do not, and the odd stream of an odd batch, run
+// alone through the same kernel, the stream in both halves.  Spectra stay planar (mono analysis is unchanged): the
 // chunk fill copies the two streams' bins into one 16-byte tile slot {A.re, B.re, A.im, B.im}, the layout of the stereo path.
+//
+// Measured (B200, batch 1024 stereo): 166-172 instead of 186 instructions per step, 758 M instead of 830 M warp
+// instructions per launch -- and 1.67 ms against 1.68 ms; mono pairs 4.94 against k_chain_direct2's 4.86 ms.  The PROBE
+// template parameter (profiling builds, -DB200S_CHAIN_PROBES) is how that was understood: removing the SFU instructions,
+// the second makeOutput, the interpolation loads or the lane hand-off changes the time by < 3 %; removing the spectrum
+// fetches and the write-back brings it to 1.01 ms.
 #pragma once
 #include "chain_direct2.cuh"
 #include "chain_direct4.cuh"

@@ -9,7 +9,8 @@
 //                       -> k_chain_t -> k_synth2 || k_commit                                        (chain_t.cuh)
 //   calls that may stretch beyond 2x additionally launch k_prep + k_chain in random-only mode: they take the streams
 //   whose blocks draw random time factors (Call::hasRandom, decided per stream by k_plan); every other CTA exits at once
-//   generic sizes (not 3072 / 2560 bands): k_analyse / k_synth (fft.cuh) and the first-generation chains
+//   generic sizes (not 3072 / 2560 bands): k_analyse / k_synth (fft.cuh), k_chain_direct2 (plain) / k_chain (mapped)
+//   selectable for A/B: k_chain_direct6 (stereo presets, tuning key 0 = 6; mono stream pairs, key 5), chain_direct6.cuh
 // Reference for every step: /root/reference/signalsmith-stretch.h (cited per kernel in kernels.cuh).
 #include <algorithm>
 #include <cmath>
