@@ -30,15 +30,14 @@ def run(name, cfg, S, C, ratio, n, chunk, gen=None, exact=1, same=False):
     print("%-40s exact=%d gen=%s maxdiff %.3g  equal=%s  (%.1fs)" % (name, exact, gen, d, np.array_equal(y, ref), time.time() - t), flush=True)
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
-GEN = int(os.environ.get("GEN", "6"))
 if which in ("all", "stereo"):
-    run("stereo small 0.8x", lambda o: o.configure(2, 512, 128), 2, 2, 0.8, 4000, 640, gen=GEN)
-    run("stereo small 0.8x 2 rounds", lambda o: o.configure(2, 512, 128), 2, 2, 0.8, 14000, 9000, gen=GEN)
-    run("stereo small 0.55x (far)", lambda o: o.configure(2, 512, 128), 2, 2, 2.4, 3000, 900, gen=GEN)
-    run("stereo L3 cheaper 1.5x", lambda o: o.presetCheaper(2, 48000.0), 2, 2, 1.5, 16000, 11520, gen=GEN)
-    run("stereo L8", lambda o: o.configure(2, 512, 64), 2, 2, 1.25, 4000, 640, gen=GEN)
-    run("stereo L1", lambda o: o.configure(2, 256, 256), 2, 2, 0.8, 6000, 1024, gen=GEN)
-    run("stereo default 0.8x 32 blocks", lambda o: o.presetDefault(2, 48000.0), 2, 2, 0.8, 2 * 57600, 46080, gen=GEN)
+    run("stereo small 0.8x", lambda o: o.configure(2, 512, 128), 2, 2, 0.8, 4000, 640, gen=6)
+    run("stereo small 0.8x 2 rounds", lambda o: o.configure(2, 512, 128), 2, 2, 0.8, 14000, 9000, gen=6)
+    run("stereo small 0.55x (far)", lambda o: o.configure(2, 512, 128), 2, 2, 2.4, 3000, 900, gen=6)
+    run("stereo L3 cheaper 1.5x", lambda o: o.presetCheaper(2, 48000.0), 2, 2, 1.5, 16000, 11520, gen=6)
+    run("stereo L8", lambda o: o.configure(2, 512, 64), 2, 2, 1.25, 4000, 640, gen=6)
+    run("stereo L1", lambda o: o.configure(2, 256, 256), 2, 2, 0.8, 6000, 1024, gen=6)
+    run("stereo default 0.8x 32 blocks", lambda o: o.presetDefault(2, 48000.0), 2, 2, 0.8, 2 * 57600, 46080, gen=6)
 if which in ("all", "mono"):
     run("mono small 1.25x (pairs)", lambda o: o.configure(1, 384, 96), 4, 1, 1.25, 9000, 8000)
     run("mono small 0.8x 3 streams", lambda o: o.configure(1, 512, 128), 3, 1, 0.8, 4000, 640)

@@ -75,17 +75,12 @@ __device__ __forceinline__ float2 make_output_fast_e(float2 phase, float energy,
 //   1: no SFU (rcp / rsqrt / sqrt replaced by one FMA)   2: the locked channel copies the leader (no second makeOutput)
 //   3: no interpolation loads (the twists use the prelim bin's input)   4: no lane-to-lane hand-off (every lane re-reads its own slots)
 //   5: the previous-input spectrum is not fetched (half the reads)   6: the finals are not written back   7: 5 + 6 + no input fetch either
-// MEMW: a second warp per CTA issues every global memory instruction of the kernel -- the chunk fills and the write-back of the
-// finals -- so that the recurrence warp never waits on them (profiles/r02_chain6_ab.md section 5: they hold the issuing warp's
-// in-order issue for ~3 300 cycles per chunk, 40 % of the kernel).  One __syncthreads per chunk hands the tiles over: the memory
-// warp writes back chunk c-1 and fills chunk c+1 while the recurrence warp computes chunk c.
-template <int LT, bool FAST, bool DUAL, int PROBE = 0, bool MEMW = false>
-__global__ void __launch_bounds__(MEMW ? 64 : 32, MEMW ? 7 : 1) k_chain_direct6(Ctx x) {
+template <int LT, bool FAST, bool DUAL, int PROBE = 0>
+__global__ void __launch_bounds__(32) k_chain_direct6(Ctx x) {
 	const Cfg &g = x.cfg;
 	const int K = g.K;
 	B200S_DYN_SHARED
 	const int lane = threadIdx.x & 31;
-	const int role = MEMW ? (int)(threadIdx.x >> 5) : 0; // MEMW: warp 0 runs the recurrence, warp 1 the memory instructions
 	// DUAL: CTA p owns streams s0 = sBase + 2p and s0 + 1.  When they share their schedule (dual_pair_ok) they run packed,
 	// stream s0 in the low halves and s0 + 1 in the high halves; otherwise (and for the odd stream of an odd batch) each
 	// runs alone with itself in both halves, one after the other -- every mono stream goes through the same arithmetic.
@@ -152,10 +147,8 @@ __global__ void __launch_bounds__(MEMW ? 64 : 32, MEMW ? 7 : 1) k_chain_direct6(
 #pragma unroll
 			for (int h = 0; h < 2; ++h) {
 				myInD[h] = spec_slot(x, sH[h], fr.inSlot, 0);
-				if (role == (MEMW ? 1 : 0)) { // (the warp that issues the fills reads these tables)
-					U.rowIn[h][lane] = myInD[h];
-					U.rowPv[h][lane] = spec_slot(x, sH[h], fr.prevSlot, 0);
-				}
+				U.rowIn[h][lane] = myInD[h];
+				U.rowPv[h][lane] = spec_slot(x, sH[h], fr.prevSlot, 0);
 				eRowD[h] = x.cE + coef_off(x, sH[h], active ? f : base, 0);
 			}
 			yBaseA = x.Y + coef_off(x, sH[0], base, 0); // mono: one row per block
@@ -163,10 +156,8 @@ __global__ void __launch_bounds__(MEMW ? 64 : 32, MEMW ? 7 : 1) k_chain_direct6(
 		} else {
 			prevInIl = base == 0 ? nullptr : il_row(x, s, prevSlotIn);
 			myInIl = il_row(x, s, fr.inSlot);
-			if (role == (MEMW ? 1 : 0)) {
-				U.rowIn[0][lane] = myInIl;
-				U.rowPv[0][lane] = il_row(x, s, fr.prevSlot);
-			}
+			U.rowIn[0][lane] = myInIl;
+			U.rowPv[0][lane] = il_row(x, s, fr.prevSlot);
 			yBaseA = x.Y + coef_off(x, s, base, 0); // stereo: two rows per block, channel 1 after channel 0
 			yBaseB = yBaseA + K;
 		}
@@ -275,6 +266,7 @@ __global__ void __launch_bounds__(MEMW ? 64 : 32, MEMW ? 7 : 1) k_chain_direct6(
 				}
 			}
 		};
+		fill(0, 0);
 		// final output of the previous block at the prelim bin of the NEXT step (read from the tile at the end of each step);
 		// for the first step: lane 0's predecessor at bin 0, nothing for the others (their q is negative)
 		c2 roN = zc;
@@ -344,8 +336,11 @@ __global__ void __launch_bounds__(MEMW ? 64 : 32, MEMW ? 7 : 1) k_chain_direct6(
 		// first step (every q <= 0: nothing behind it is inside the spectrum, but the masks need their indices)
 		if (farAny) preload(-G * lane, std::true_type{}, std::false_type{}, false);
 		else preload(-G * lane, std::false_type{}, std::false_type{}, false);
-		// one chunk of the recurrence: CHAIN_CH steps on the tiles of buffer cb
-		auto run_one_chunk = [&](const int k0, const int cb) {
+		int cb = 0; // buffer of the chunk being computed
+		for (int k0 = 0; k0 < steps; k0 += CHAIN_CH, cb ^= 1) {
+			cp_async_wait_all(); // this chunk's tiles (issued one chunk ago)
+			__syncwarp();
+			if (k0 + CHAIN_CH < steps) fill(k0 + CHAIN_CH, cb ^ 1); // next chunk: in flight during the 8 steps below
 			// ---------------- CHAIN_CH steps ----------------
 			// INTERIOR: every lane's q, b and interpolation points are inside [0, K) for the whole chunk, so all the
 			// edge masks below are identities and are compiled out (about nine chunks in ten)
@@ -501,55 +496,27 @@ __global__ void __launch_bounds__(MEMW ? 64 : 32, MEMW ? 7 : 1) k_chain_direct6(
 			if (farAny) run_chunk(std::true_type{}, std::false_type{});
 			else if (k0 >= interiorFrom && k0 + CHAIN_CH <= K) run_chunk(std::false_type{}, std::true_type{});
 			else run_chunk(std::false_type{}, std::false_type{});
-		};
-		// ---------------- write a chunk's finals back: planar Band::output rows, 32 B per row and quarter-warp;
-		//                  all tile reads first, then the stores (row addresses are arithmetic).
-		// (Measured dead end, round 2: every lane storing its own final straight to its row in every step -- 64 partial-
-		//  sector writes per warp and step instead of 16 full-sector stores per chunk: 2.62 ms against 1.68 ms.)
-		auto write_back = [&](const int k0, const int cb) {
-			float4 v[8];
+			// ---------------- write the chunk's finals back: planar Band::output rows, 32 B per row and quarter-warp;
+			//                  all tile reads first, then the stores (row addresses are arithmetic).
+			// (Measured dead end, round 2: every lane storing its own final straight to its row in every step -- 64 partial-
+			//  sector writes per warp and step instead of 16 full-sector stores per chunk: 2.62 ms against 1.68 ms.)
+			{
+				float4 v[8];
 #pragma unroll
-			for (int it = 0; it < 8; ++it) v[it] = U.pvy[cb][fillI][fillF + 4 * it];
-			const int rowMul = DUAL ? 1 : 2; // rows per block in Y
+				for (int it = 0; it < 8; ++it) v[it] = U.pvy[cb][fillI][fillF + 4 * it];
+				const int rowMul = DUAL ? 1 : 2; // rows per block in Y
 #pragma unroll
-			for (int it = 0; it < 8; ++it) {
-				const int fl = fillF + 4 * it;
-				const int b = k0 + fillI - G * fl - LT - 1;
-				if (PROBE != 6 && PROBE != 7 && fl < nAct && (unsigned)b < (unsigned)K) {
-					const size_t o = (size_t)(rowMul * fl) * K + b;
-					yBaseA[o] = make_float2(v[it].x, v[it].z);
-					yBaseB[o] = make_float2(v[it].y, v[it].w);
+				for (int it = 0; it < 8; ++it) {
+					const int fl = fillF + 4 * it;
+					const int b = k0 + fillI - G * fl - LT - 1;
+					if (PROBE != 6 && PROBE != 7 && fl < nAct && (unsigned)b < (unsigned)K) {
+						const size_t o = (size_t)(rowMul * fl) * K + b;
+						yBaseA[o] = make_float2(v[it].x, v[it].z);
+						yBaseB[o] = make_float2(v[it].y, v[it].w);
+					}
 				}
 			}
-		};
-		if constexpr (!MEMW) {
-			fill(0, 0);
-			int cb = 0; // buffer of the chunk being computed
-			for (int k0 = 0; k0 < steps; k0 += CHAIN_CH, cb ^= 1) {
-				cp_async_wait_all(); // this chunk's tiles (issued one chunk ago)
-				__syncwarp();
-				if (k0 + CHAIN_CH < steps) fill(k0 + CHAIN_CH, cb ^ 1); // next chunk: in flight during the 8 steps below
-				run_one_chunk(k0, cb);
-				write_back(k0, cb);
-				__syncwarp();
-			}
-		} else {
-			// iteration c: the recurrence warp computes chunk c (tiles of buffer cb, filled during iteration c-1); the memory
-			// warp writes back chunk c-1 (buffer cb^1, complete since the barrier) and then refills that buffer and the
-			// spectrum window for chunk c+1.  One more iteration for the last write-back.
-			if (role == 1) fill(0, 0);
-			int cb = 0;
-			for (int k0 = 0; k0 < steps + CHAIN_CH; k0 += CHAIN_CH, cb ^= 1) {
-				if (role == 1) cp_async_wait_all(); // the tiles of chunk k0 have landed ...
-				__syncthreads();                    // ... and are visible to the recurrence warp, whose chunk k0 - 8 is complete
-				if (role == 0) {
-					if (k0 < steps) run_one_chunk(k0, cb);
-				} else {
-					if (k0 > 0) write_back(k0 - CHAIN_CH, cb ^ 1);
-					if (k0 + CHAIN_CH < steps) fill(k0 + CHAIN_CH, cb ^ 1);
-				}
-			}
-			__syncthreads(); // the tiles are free for the next group of blocks
+			__syncwarp();
 		}
 	}
 	__syncwarp();

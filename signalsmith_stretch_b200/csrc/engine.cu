@@ -359,34 +359,19 @@ static ChainKernel chain6_kernel(int L) {
 	default: return k_chain_direct6<8, FAST, DUAL>;
 	}
 }
-// generation 7: k_chain_direct6 with a memory warp beside the recurrence warp (64 threads per stream / stream pair)
-template <bool FAST, bool DUAL>
-static ChainKernel chain6m_kernel(int L) {
-	switch (L) {
-	case 1: return k_chain_direct6<1, FAST, DUAL, 0, true>;
-	case 2: return k_chain_direct6<2, FAST, DUAL, 0, true>;
-	case 3: return k_chain_direct6<3, FAST, DUAL, 0, true>;
-	case 4: return k_chain_direct6<4, FAST, DUAL, 0, true>;
-	case 5: return k_chain_direct6<5, FAST, DUAL, 0, true>;
-	case 6: return k_chain_direct6<6, FAST, DUAL, 0, true>;
-	case 7: return k_chain_direct6<7, FAST, DUAL, 0, true>;
-	default: return k_chain_direct6<8, FAST, DUAL, 0, true>;
-	}
-}
 // mono plain path: pairs of streams on the packed wavefront (k_chain_direct6<.., DUAL>) instead of k_chain_direct2.  Off by
 // default: measured on B200 (profiles/r02_chain6_ab.md) it is no faster (4.99 vs 4.85 ms for 4096 streams) although it issues
 // 40 % fewer instructions per stream -- the wavefront kernels are bound by dependent latency at 7 warps per SM, not by issue.
 // B200S_DUAL=1 / b200s_set_tuning(e, 5, 1) switch it on (cross-check in the tests).
-static int dual_mode() {
+static bool dual_enabled() {
 	static int env = -1;
 	if (env < 0) {
 		const char *v = getenv("B200S_DUAL");
-		env = v ? atoi(v) : 0;
+		env = v ? (atoi(v) != 0) : 0;
 	}
-	return env;
+	return env != 0;
 }
 static ChainKernel chain3_kernel(const Cfg &g, int v, bool fast) {
-	if (v >= 7) return fast ? chain6m_kernel<true, false>(g.L) : chain6m_kernel<false, false>(g.L);
 #ifdef B200S_CHAIN_PROBES // profiling builds only: ablations of k_chain_direct6 (wrong results), B200S_CHAIN_PROBE=1..7
 	if (v >= 6 && fast && g.L == 4) {
 		static int probe = -1;
@@ -655,8 +640,6 @@ static int configure_impl(b200s_engine *e, int channels, int block, int interval
 	// k_chain_direct6: seven one-warp CTAs of 31.5 KB per SM need the full shared-memory carve-out
 	CK(cudaFuncSetAttribute(g.C == 1 ? chain6_kernel<true, true>(g.L) : chain6_kernel<true, false>(g.L), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 	CK(cudaFuncSetAttribute(g.C == 1 ? chain6_kernel<false, true>(g.L) : chain6_kernel<false, false>(g.L), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-	CK(cudaFuncSetAttribute(g.C == 1 ? chain6m_kernel<true, true>(g.L) : chain6m_kernel<true, false>(g.L), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-	CK(cudaFuncSetAttribute(g.C == 1 ? chain6m_kernel<false, true>(g.L) : chain6m_kernel<false, false>(g.L), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 	if (use_pair_fft(g)) {
 		CK(cudaFuncSetAttribute(analyse2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_analyse2(g)));
 		CK(cudaFuncSetAttribute(synth2_kernel(g), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_synth2(g)));
@@ -907,17 +890,15 @@ static int process_impl(b200s_engine *e, const float *dIn, int inChanStride, lon
 					if ((_rc = prof_mark(e, PK_CHAIN, false))) return _rc;
 #endif
 				} else if (plain && chainV >= 3) {
-					PROF(PK_CHAIN, B200S_LAUNCH(chain3_kernel(g, chainV, !e->exactMath), dim3(x.sCount), dim3(chainV >= 7 ? 64 : 32), chainV >= 6 ? smem_chain6() : chainV == 4 ? smem_chain4(g.L) : sizeof(Chain3Tiles), st, x));
+					PROF(PK_CHAIN, B200S_LAUNCH(chain3_kernel(g, chainV, !e->exactMath), dim3(x.sCount), dim3(32), chainV >= 6 ? smem_chain6() : chainV == 4 ? smem_chain4(g.L) : sizeof(Chain3Tiles), st, x));
 				} else if (plain && chainV == 2) {
 					const int W = chain2_warps(g, nOut);
 					ChainKernel kc = chain2_kernel(g, g.C == 1 && !e->exactMath);
 					int _rc;
 					if ((_rc = prof_mark(e, PK_CHAIN, true))) return _rc;
-					if (g.C == 1 && (e->dual < 0 ? dual_mode() : e->dual) != 0) { // mono: two streams per warp on the packed wavefront
-						const bool memw = (e->dual < 0 ? dual_mode() : e->dual) >= 2; // 2: with the memory warp (generation 7)
-						ChainKernel kd = memw ? (e->exactMath ? chain6m_kernel<false, true>(g.L) : chain6m_kernel<true, true>(g.L))
-						                      : (e->exactMath ? chain6_kernel<false, true>(g.L) : chain6_kernel<true, true>(g.L));
-						B200S_LAUNCH(kd, dim3((x.sCount + 1) / 2), dim3(memw ? 64 : 32), smem_chain6(), st, x);
+					if (g.C == 1 && (e->dual < 0 ? dual_enabled() : e->dual != 0)) { // mono: two streams per warp on the packed wavefront
+						ChainKernel kd = e->exactMath ? chain6_kernel<false, true>(g.L) : chain6_kernel<true, true>(g.L);
+						B200S_LAUNCH(kd, dim3((x.sCount + 1) / 2), dim3(32), smem_chain6(), st, x);
 					} else {
 						B200S_LAUNCH(kc, dim3(x.sCount), dim3(32 * W), smem_chain2(g.C, W), st, x);
 					}
@@ -1176,7 +1157,7 @@ int b200s_set_sub_batches(b200s_engine *e, int n) {
 }
 int b200s_set_tuning(b200s_engine *e, int key, int value) {
 	if (!e) return B200S_EINVAL;
-	if (key == 0 && value >= 0 && value <= 7) {
+	if (key == 0 && value >= 0 && value <= 6) {
 #ifndef B200S_KEEP_OLD_KERNELS
 		if (value == 1 || value == 3 || value == 5) {
 			e->err = "b200s_set_tuning: chain generations 1, 3 and 5 are superseded and not part of this build (-DB200S_KEEP_OLD_KERNELS)";
@@ -1189,7 +1170,7 @@ int b200s_set_tuning(b200s_engine *e, int key, int value) {
 	else if (key == 2 && value >= 1) e->nHostParts = std::min(value, (int)b200s_engine::kMaxSub);
 	else if (key == 3 && (value == 0 || value == 1)) e->exactMath = value;
 	else if (key == 4 && (value == 0 || value == 1)) e->stepMajor = value;
-	else if (key == 5 && value >= 0 && value <= 2) e->dual = value;
+	else if (key == 5 && (value == 0 || value == 1)) e->dual = value;
 	else {
 		e->err = "b200s_set_tuning: unknown key or value";
 		return B200S_EINVAL;

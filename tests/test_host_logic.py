@@ -69,7 +69,7 @@ def _emu(path, batch, exact_math=True, gen=0, pairs=False):
     if gen:
         e.set_tuning(0, gen)  # generation of the stereo direct chain kernel (0 = the default)
     if pairs:
-        e.set_tuning(5, int(pairs))  # mono plain path: two streams per warp on the packed wavefront (k_chain_direct6<.., DUAL>)
+        e.set_tuning(5, 1)  # mono plain path: two streams per warp on the packed wavefront (k_chain_direct6<.., DUAL>)
     return e
 
 
@@ -419,7 +419,7 @@ def test_randomised_configurations_bit_exact_vs_oracle(emu_libs, oracle_port):
         assert np.array_equal(y, ref), (it, preset, C, sr, split, ratio, semis, ton, form, chunk, float(np.abs(y - ref).max()))
 
 
-@pytest.mark.parametrize("gen", [4, 6, 7])
+@pytest.mark.parametrize("gen", [4, 6])
 @pytest.mark.parametrize("idx", [0, 3, 4, 5])
 def test_stereo_chain_generations_bit_exact_vs_oracle(emu_libs, oracle_port, gen, idx):
     """Both packed stereo chain kernels (k_chain_direct4 and its leaner successor k_chain_direct6, which forms the twists
@@ -440,7 +440,7 @@ def test_stereo_chain_generation6_with_diverging_streams_and_silence(emu_libs, o
     S, C, calls, n = 3, 2, 7, 5760
     x = signals.batch("harmonic", S, C, calls * n, 48000)
     x[1, :, 2 * n:5 * n] = 0.0
-    g = _emu(emu_libs["exact"], S, gen=7)
+    g = _emu(emu_libs["exact"], S, gen=6)
     g.presetDefault(C, 48000.0)
     y = signals.run_batch(g, x, 0.8, int(n * 0.8))
     ref = _oracle_batch(oracle_port, lambda o: o.presetDefault(C, 48000.0), x, 0.8, int(n * 0.8))
@@ -459,7 +459,7 @@ def test_mono_stream_pairs_on_the_packed_chain_bit_exact_vs_oracle(emu_libs, ora
     S = 5  # two pairs and an odd stream
     x = signals.batch("harmonic", S, 1, 12 * B, 48000)
     x[3, :, 3 * B:7 * B] = 0.0  # stream 3 falls silent for a while: the pair (2, 3) stops sharing its schedule
-    g = _emu(emu_libs["exact"], S, pairs=2 if name in ("L3", "L4") else 1)  # (2: with the memory warp)
+    g = _emu(emu_libs["exact"], S, pairs=True)
     g.configure(1, B, H)
     chunk = 40 * H + 17  # more than 32 blocks per call: a second group of lanes
     y = signals.run_batch(g, x, ratio, chunk)
