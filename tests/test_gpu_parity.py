@@ -311,9 +311,9 @@ def test_chain_kernel_generations_agree_bit_exactly(gpu, blocks_per_call):
 @pytest.mark.gpu
 @pytest.mark.parametrize("preset,ratio", [("presetDefault", 0.8), ("presetCheaper", 2.0)])
 def test_mono_stream_pairs_agree_with_one_stream_per_warp_bit_exactly(gpu, preset, ratio):
-    """Mono plain path: pairs of streams on the packed wavefront (k_chain_direct6<.., DUAL>; stream 4 of the five stays on
-    k_chain_direct2, and so does the pair (2, 3) while stream 3 is silent) against every stream on k_chain_direct2, exact
-    arithmetic: identical bit for bit.  40 blocks per call: a second group of lanes."""
+    """Mono plain path: two streams per warp on the packed wavefront (k_chain_direct6<.., DUAL>, tuning key 5; stream 4 of the
+    five, and the pair (2, 3) while stream 3 is silent, run alone through the same kernel) against every stream on
+    k_chain_direct2, exact arithmetic: identical bit for bit.  40 blocks per call: a second group of lanes."""
     outs = []
     for dual in (0, 1):
         e = gpu(5)
